@@ -1,0 +1,415 @@
+"""hprlp_b200 -- ctypes mirror of the HPR-LP C ABI (include/HPRLP.h, include/batched_solver.h,
+include/hprlp_b200.h) for tests and bench.py.
+
+The product is the C-ABI shared library ``lib/libhprlp.so`` (CUDA, sm_100a); this module only
+declares the struct layouts and function signatures, exactly as the reference's Julia wrapper does
+(reference bindings/julia/package/src/wrapper.jl:92-164).  It also knows how to load, side by
+side, the reference's own CUDA build (``oracle/_ref/libhprlp_ref.so``, same seven symbols), the CPU
+oracle (``oracle/liboracle.so``) and the synthetic LP generator (``tools/libsynth.so``) -- those three
+are test/bench infrastructure, never used by the product path.
+
+There is no CPU fallback: loading or calling the engine without the CUDA library / a GPU raises.
+The directory is named ``hpr-lp-c_b200``; import it with ``__graft_entry__.load_package()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = ROOT / "lib" / "libhprlp.so"
+REF_LIB_PATH = ROOT / "oracle" / "_ref" / "libhprlp_ref.so"
+ORACLE_LIB_PATH = ROOT / "oracle" / "liboracle.so"
+SYNTH_LIB_PATH = ROOT / "tools" / "libsynth.so"
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+# ---------------------------------------------------------------------------------------------
+# struct mirrors (include/structs.h)
+# ---------------------------------------------------------------------------------------------
+class SparseMatrix(C.Structure):
+    _fields_ = [("row", C.c_int), ("col", C.c_int), ("numElements", C.c_int),
+                ("colIndex", c_int_p), ("rowPtr", c_int_p), ("value", c_double_p)]
+
+
+class Parameters(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("stop_tol", C.c_double), ("time_limit", C.c_double),
+                ("device_number", C.c_int), ("check_iter", C.c_int),
+                ("CUSPARSE_spmv", C.c_bool), ("autotune_verbose", C.c_bool),
+                ("use_CR_scaling", C.c_bool), ("use_Ruiz_scaling", C.c_bool),
+                ("use_Pock_Chambolle_scaling", C.c_bool), ("use_bc_scaling", C.c_bool),
+                ("use_presolve", C.c_bool)]
+
+    @classmethod
+    def default(cls, **kw):
+        p = cls(2**31 - 1, 1e-4, 3600.0, 0, 150, False, False, True, True, True, True, True)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+
+class Results(C.Structure):
+    _fields_ = [("residuals", C.c_double), ("primal_obj", C.c_double), ("gap", C.c_double),
+                ("time4", C.c_double), ("time6", C.c_double), ("time8", C.c_double), ("time", C.c_double),
+                ("iter4", C.c_int), ("iter6", C.c_int), ("iter8", C.c_int), ("iter", C.c_int),
+                ("status", C.c_char * 64),
+                ("x", c_double_p), ("y", c_double_p), ("z", c_double_p)]
+
+
+class BatchedResults(C.Structure):
+    _fields_ = [("m", C.c_int), ("n", C.c_int), ("batch_size", C.c_int),
+                ("x", c_double_p), ("y", c_double_p), ("z", c_double_p),
+                ("primal_obj", c_double_p), ("residuals", c_double_p), ("gap", c_double_p),
+                ("iter", c_int_p), ("status", C.POINTER(C.c_char)),
+                ("time", C.c_double), ("setup_time", C.c_double), ("solve_time", C.c_double),
+                ("power_time", C.c_double)]
+
+
+class LPInfoCpu(C.Structure):
+    _fields_ = [("m", C.c_int), ("n", C.c_int), ("A", C.POINTER(SparseMatrix)),
+                ("AL", c_double_p), ("AU", c_double_p), ("c", c_double_p),
+                ("l", c_double_p), ("u", c_double_p), ("obj_constant", C.c_double)]
+
+
+class B200Info(C.Structure):
+    _fields_ = [("lambda_max", C.c_double), ("sigma", C.c_double),
+                ("setup_seconds", C.c_double), ("scaling_seconds", C.c_double), ("power_seconds", C.c_double),
+                ("loop_device_ms", C.c_double), ("restarts", C.c_int), ("power_iters", C.c_int),
+                ("kernel_launches", C.c_longlong),
+                ("b_scale", C.c_double), ("c_scale", C.c_double), ("norm_b", C.c_double), ("norm_c", C.c_double),
+                ("norm_b_org", C.c_double), ("norm_c_org", C.c_double),
+                ("lanes_A", C.c_int), ("lanes_AT", C.c_int), ("items_A", C.c_int), ("items_AT", C.c_int)]
+
+
+REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve", "free_model",
+                     "HPRLP_main_solve", "solve_batched", "free_batched_results"]
+EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
+                    "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
+                    "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
+                    "hprlp_b200_version"]
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class HprLib:
+    """One loaded libhprlp (ours or the reference build): the seven reference symbols."""
+
+    def __init__(self, path, extended=False):
+        path = Path(path)
+        if not path.exists():
+            raise FileNotFoundError(f"{path} not built (run __graft_entry__.build())")
+        self.path = path
+        self.lib = C.CDLL(str(path), mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
+        L = self.lib
+        L.create_model_from_arrays.restype = C.POINTER(LPInfoCpu)
+        L.create_model_from_arrays.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p,
+                                               c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_bool]
+        L.create_model_from_mps.restype = C.POINTER(LPInfoCpu)
+        L.create_model_from_mps.argtypes = [C.c_char_p]
+        L.solve.restype = Results
+        L.solve.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)]
+        L.HPRLP_main_solve.restype = Results
+        L.HPRLP_main_solve.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)]
+        L.free_model.restype = None
+        L.free_model.argtypes = [C.POINTER(LPInfoCpu)]
+        L.solve_batched.restype = BatchedResults
+        L.solve_batched.argtypes = [C.POINTER(LPInfoCpu), C.c_int, c_double_p, c_double_p, c_double_p,
+                                    c_double_p, c_double_p, c_double_p, C.POINTER(Parameters)]
+        L.free_batched_results.restype = None
+        L.free_batched_results.argtypes = [C.POINTER(BatchedResults)]
+        self.extended = extended
+        if extended:
+            L.hprlp_b200_solve_ex.restype = Results
+            L.hprlp_b200_solve_ex.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), c_double_p, C.c_int, c_int_p,
+                                              c_double_p, c_double_p, c_double_p, C.c_int, C.POINTER(B200Info)]
+            L.hprlp_b200_power_start.restype = C.c_int
+            L.hprlp_b200_power_start.argtypes = [C.c_int, C.c_int, c_double_p]
+            L.hprlp_b200_engine_create.restype = C.c_void_p
+            L.hprlp_b200_engine_create.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)]
+            L.hprlp_b200_engine_run.restype = C.c_double
+            L.hprlp_b200_engine_run.argtypes = [C.c_void_p, C.c_int]
+            L.hprlp_b200_engine_time_phase.restype = C.c_double
+            L.hprlp_b200_engine_time_phase.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            L.hprlp_b200_engine_residuals.restype = C.c_int
+            L.hprlp_b200_engine_residuals.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+            L.hprlp_b200_engine_info.restype = None
+            L.hprlp_b200_engine_info.argtypes = [C.c_void_p, C.POINTER(B200Info)]
+            L.hprlp_b200_engine_destroy.restype = None
+            L.hprlp_b200_engine_destroy.argtypes = [C.c_void_p]
+            L.hprlp_b200_scale_only.restype = C.c_int
+            L.hprlp_b200_scale_only.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)] + [c_double_p, c_int_p, c_int_p] + \
+                [c_double_p] * 9
+            L.hprlp_b200_version.restype = C.c_char_p
+
+    # -- model layer -----------------------------------------------------------------------------
+    def create_model(self, lp, is_csc=False):
+        """lp: dict with m,n,rowPtr,colIndex,values,AL,AU,l,u,c (numpy)."""
+        keep = {k: (_i32(lp[k]) if k in ("rowPtr", "colIndex") else _f64(lp[k]))
+                for k in ("rowPtr", "colIndex", "values", "AL", "AU", "l", "u", "c")}
+        nnz = int(keep["values"].shape[0])
+        model = self.lib.create_model_from_arrays(int(lp["m"]), int(lp["n"]), nnz, _ip(keep["rowPtr"]), _ip(keep["colIndex"]),
+                                                  _dp(keep["values"]), _dp(keep["AL"]), _dp(keep["AU"]), _dp(keep["l"]),
+                                                  _dp(keep["u"]), _dp(keep["c"]), bool(is_csc))
+        return model
+
+    def create_model_from_mps(self, path):
+        return self.lib.create_model_from_mps(str(path).encode())
+
+    def free_model(self, model):
+        self.lib.free_model(model)
+
+    @staticmethod
+    def model_arrays(model):
+        """Copy the arrays of an LP_info_cpu* back to numpy (for bit-exact model comparisons)."""
+        mm = model.contents
+        A = mm.A.contents
+        m, n, nnz = mm.m, mm.n, A.numElements
+        return dict(m=m, n=n, nnz=nnz,
+                    rowPtr=np.ctypeslib.as_array(A.rowPtr, (m + 1,)).copy(),
+                    colIndex=np.ctypeslib.as_array(A.colIndex, (nnz,)).copy(),
+                    values=np.ctypeslib.as_array(A.value, (nnz,)).copy(),
+                    AL=np.ctypeslib.as_array(mm.AL, (m,)).copy(), AU=np.ctypeslib.as_array(mm.AU, (m,)).copy(),
+                    c=np.ctypeslib.as_array(mm.c, (n,)).copy(), l=np.ctypeslib.as_array(mm.l, (n,)).copy(),
+                    u=np.ctypeslib.as_array(mm.u, (n,)).copy(), obj_constant=mm.obj_constant)
+
+    # -- solve -------------------------------------------------------------------------------------
+    def _take(self, res, m, n):
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        out = dict(status=res.status.decode(), iter=res.iter, residuals=res.residuals, primal_obj=res.primal_obj,
+                   gap=res.gap, time=res.time, time4=res.time4, iter4=res.iter4)
+        for name, ln in (("x", n), ("y", m), ("z", n)):
+            p = getattr(res, name)
+            out[name] = np.ctypeslib.as_array(p, (ln,)).copy() if p else None
+            if p:
+                libc.free(C.cast(p, C.c_void_p))
+        return out
+
+    def solve(self, model, param=None, main=False):
+        mm = model.contents
+        fn = self.lib.HPRLP_main_solve if main else self.lib.solve
+        res = fn(model, C.byref(param) if param is not None else None)
+        return self._take(res, mm.m, mm.n)
+
+    def solve_ex(self, model, param, power_z0=None, trace_iters=(), quiet=True):
+        assert self.extended
+        mm = model.contents
+        m, n = mm.m, mm.n
+        ti = _i32(list(trace_iters))
+        nt = int(ti.shape[0])
+        tx = np.zeros((max(nt, 1), n)); ty = np.zeros((max(nt, 1), m)); tz = np.zeros((max(nt, 1), n))
+        z0 = _f64(power_z0) if power_z0 is not None else None
+        info = B200Info()
+        res = self.lib.hprlp_b200_solve_ex(model, C.byref(param), _dp(z0), nt, _ip(ti), _dp(tx), _dp(ty), _dp(tz),
+                                           1 if quiet else 0, C.byref(info))
+        out = self._take(res, m, n)
+        out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
+        out["trace"] = {int(k): (tx[i].copy(), ty[i].copy(), tz[i].copy()) for i, k in enumerate(ti)}
+        return out
+
+    def power_start(self, m, device=0):
+        out = np.zeros(m)
+        rc = self.lib.hprlp_b200_power_start(int(m), int(device), _dp(out))
+        if rc != 0:
+            raise RuntimeError("hprlp_b200_power_start failed")
+        return out
+
+    def scale_only(self, model, param):
+        mm = model.contents
+        m, n, nnz = mm.m, mm.n, mm.A.contents.numElements
+        o = dict(A_val=np.zeros(nnz), AT_rowPtr=np.zeros(n + 1, np.int32), AT_col=np.zeros(nnz, np.int32),
+                 AT_val=np.zeros(nnz), AL=np.zeros(m), AU=np.zeros(m), l=np.zeros(n), u=np.zeros(n), c=np.zeros(n),
+                 row_norm=np.zeros(m), col_norm=np.zeros(n), scalars=np.zeros(6))
+        rc = self.lib.hprlp_b200_scale_only(model, C.byref(param), _dp(o["A_val"]), _ip(o["AT_rowPtr"]), _ip(o["AT_col"]),
+                                            _dp(o["AT_val"]), _dp(o["AL"]), _dp(o["AU"]), _dp(o["l"]), _dp(o["u"]), _dp(o["c"]),
+                                            _dp(o["row_norm"]), _dp(o["col_norm"]), _dp(o["scalars"]))
+        if rc != 0:
+            raise RuntimeError("hprlp_b200_scale_only failed")
+        return o
+
+    def solve_batched(self, model, C_, AL, AU, l, u, obj_constants=None, param=None):
+        """Dense inputs column-major: arrays of shape (B, n) / (B, m) in C order == n x B column-major."""
+        mm = model.contents
+        m, n = mm.m, mm.n
+        C_, AL, AU, l, u = (_f64(a) for a in (C_, AL, AU, l, u))
+        B = C_.shape[0]
+        oc = _f64(obj_constants) if obj_constants is not None else None
+        res = self.lib.solve_batched(model, B, _dp(C_), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(oc),
+                                     C.byref(param) if param is not None else None)
+        out = dict(m=res.m, n=res.n, batch_size=res.batch_size, time=res.time, setup_time=res.setup_time,
+                   solve_time=res.solve_time, power_time=res.power_time)
+        if res.status:
+            raw = C.string_at(res.status, 64 * B)
+            out["status"] = [raw[64 * k:64 * k + 64].split(b"\0")[0].decode() for k in range(B)]
+        if res.x:
+            out["x"] = np.ctypeslib.as_array(res.x, (B, n)).copy()
+            out["y"] = np.ctypeslib.as_array(res.y, (B, m)).copy()
+            out["z"] = np.ctypeslib.as_array(res.z, (B, n)).copy()
+            out["primal_obj"] = np.ctypeslib.as_array(res.primal_obj, (B,)).copy()
+            out["residuals"] = np.ctypeslib.as_array(res.residuals, (B,)).copy()
+            out["gap"] = np.ctypeslib.as_array(res.gap, (B,)).copy()
+            out["iter"] = np.ctypeslib.as_array(res.iter, (B,)).copy()
+        self.lib.free_batched_results(C.byref(res))
+        return out
+
+
+_cache = {}
+
+
+def load_engine():
+    """The product library. Raises if it is not built -- there is no fallback."""
+    if "eng" not in _cache:
+        _cache["eng"] = HprLib(LIB_PATH, extended=True)
+    return _cache["eng"]
+
+
+def load_reference():
+    """The reference's own CUDA build (oracle/_ref), test/bench infrastructure."""
+    if "ref" not in _cache:
+        _cache["ref"] = HprLib(REF_LIB_PATH, extended=False)
+    return _cache["ref"]
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle (oracle/hpr_oracle.c) -- test infrastructure only
+# ---------------------------------------------------------------------------------------------
+class OracleParams(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("stop_tol", C.c_double), ("time_limit", C.c_double), ("check_iter", C.c_int),
+                ("use_cr", C.c_int), ("use_ruiz", C.c_int), ("use_pc", C.c_int), ("use_bc", C.c_int)]
+
+
+class OracleInfo(C.Structure):
+    _fields_ = [(k, C.c_double) for k in "residuals primal_obj dual_obj gap err_rp err_rd".split()] + \
+               [("iter", C.c_int), ("status", C.c_char * 64), ("lambda_max", C.c_double), ("sigma", C.c_double),
+                ("restarts", C.c_int)] + \
+               [(k, C.c_double) for k in "b_scale c_scale norm_b norm_c norm_b_org norm_c_org".split()] + \
+               [("power_iters", C.c_int), ("solve_seconds", C.c_double)]
+
+
+class Oracle:
+    def __init__(self):
+        if not ORACLE_LIB_PATH.exists():
+            raise FileNotFoundError(f"{ORACLE_LIB_PATH} not built (make -C oracle liboracle.so)")
+        self.lib = C.CDLL(str(ORACLE_LIB_PATH))
+        self.lib.oracle_power.restype = C.c_double
+
+    @staticmethod
+    def params_from(param: Parameters):
+        return OracleParams(param.max_iter, param.stop_tol, param.time_limit, param.check_iter,
+                            int(param.use_CR_scaling), int(param.use_Ruiz_scaling),
+                            int(param.use_Pock_Chambolle_scaling), int(param.use_bc_scaling))
+
+    def solve(self, lp, param: Parameters, power_z0=None, trace_iters=(), obj_constant=0.0):
+        m, n = int(lp["m"]), int(lp["n"])
+        rp, ci, v = _i32(lp["rowPtr"]), _i32(lp["colIndex"]), _f64(lp["values"])
+        AL, AU, l, u, c = (_f64(lp[k]) for k in ("AL", "AU", "l", "u", "c"))
+        x, y, z = np.zeros(n), np.zeros(m), np.zeros(n)
+        ti = _i32(list(trace_iters)); nt = int(ti.shape[0])
+        tx = np.zeros((max(nt, 1), n)); ty = np.zeros((max(nt, 1), m)); tz = np.zeros((max(nt, 1), n))
+        z0 = _f64(power_z0) if power_z0 is not None else None
+        info = OracleInfo()
+        op = self.params_from(param)
+        self.lib.oracle_solve(m, n, _ip(rp), _ip(ci), _dp(v), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(c),
+                              C.c_double(obj_constant), C.byref(op), _dp(z0), _dp(x), _dp(y), _dp(z), C.byref(info),
+                              nt, _ip(ti), _dp(tx), _dp(ty), _dp(tz))
+        out = dict(status=info.status.decode(), iter=info.iter, residuals=info.residuals, primal_obj=info.primal_obj,
+                   dual_obj=info.dual_obj, gap=info.gap, x=x, y=y, z=z,
+                   info={f[0]: getattr(info, f[0]) for f in OracleInfo._fields_ if f[0] != "status"},
+                   trace={int(k): (tx[i].copy(), ty[i].copy(), tz[i].copy()) for i, k in enumerate(ti)})
+        return out
+
+    def transpose(self, rows, cols, rp, ci, v):
+        rp, ci, v = _i32(rp), _i32(ci), _f64(v)
+        nnz = int(v.shape[0])
+        trp = np.zeros(cols + 1, np.int32); tci = np.zeros(nnz, np.int32); tv = np.zeros(nnz)
+        self.lib.oracle_transpose(int(rows), int(cols), nnz, _ip(rp), _ip(ci), _dp(v), _ip(trp), _ip(tci), _dp(tv))
+        return trp, tci, tv
+
+    def scale(self, lp, param: Parameters):
+        m, n = int(lp["m"]), int(lp["n"])
+        rp, ci = _i32(lp["rowPtr"]), _i32(lp["colIndex"])
+        v = _f64(lp["values"]).copy()
+        AL, AU, l, u, c = (_f64(lp[k]).copy() for k in ("AL", "AU", "l", "u", "c"))
+        nnz = int(v.shape[0])
+        o = dict(AT_rowPtr=np.zeros(n + 1, np.int32), AT_col=np.zeros(nnz, np.int32), AT_val=np.zeros(nnz),
+                 row_norm=np.zeros(m), col_norm=np.zeros(n), scalars=np.zeros(6))
+        op = self.params_from(param)
+        self.lib.oracle_scale(m, n, _ip(rp), _ip(ci), _dp(v), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(c), C.byref(op),
+                              _ip(o["AT_rowPtr"]), _ip(o["AT_col"]), _dp(o["AT_val"]), _dp(o["row_norm"]), _dp(o["col_norm"]),
+                              _dp(o["scalars"]))
+        o.update(A_val=v, AL=AL, AU=AU, l=l, u=u, c=c)
+        return o
+
+
+def load_oracle():
+    if "oracle" not in _cache:
+        _cache["oracle"] = Oracle()
+    return _cache["oracle"]
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic LPs (tools/synth_lp.c)
+# ---------------------------------------------------------------------------------------------
+SEED = 20251018
+
+
+def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
+    """kind: 'uniform' | 'powerlaw'. Returns the dict create_model() takes (+ x*,y*,z*,obj*)."""
+    if not SYNTH_LIB_PATH.exists():
+        raise FileNotFoundError(f"{SYNTH_LIB_PATH} not built")
+    L = C.CDLL(str(SYNTH_LIB_PATH))
+    L.synth_lp_rowptr.restype = C.c_longlong
+    L.synth_lp_rowptr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_uint64, c_int_p]
+    L.synth_lp_matrix_rows.restype = None
+    L.synth_lp_matrix_rows.argtypes = [C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
+    L.synth_lp_vectors.restype = C.c_double
+    L.synth_lp_vectors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, C.c_uint64, C.c_uint64] + [c_double_p] * 8
+    k = {"uniform": 0, "powerlaw": 1}[kind]
+    rp = np.zeros(m + 1, np.int32)
+    tot = L.synth_lp_rowptr(k, m, n, int(nnz), seed, _ip(rp))
+    col = np.zeros(tot, np.int32); val = np.zeros(tot)
+    L.synth_lp_matrix_rows(n, seed, _ip(rp), 0, m, _ip(col), _dp(val))
+    lp = dict(m=m, n=n, rowPtr=rp, colIndex=col, values=val)
+    lp.update(synth_vectors(lp, seed, seed if vec_seed is None else vec_seed, _lib=L))
+    if not with_solution:
+        for kx in ("xs", "ys", "zs"):
+            lp.pop(kx)
+    return lp
+
+
+def synth_vectors(lp, seed=SEED, vec_seed=SEED, _lib=None):
+    L = _lib or C.CDLL(str(SYNTH_LIB_PATH))
+    if _lib is None:
+        L.synth_lp_vectors.restype = C.c_double
+        L.synth_lp_vectors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, C.c_uint64, C.c_uint64] + [c_double_p] * 8
+    m, n = lp["m"], lp["n"]
+    AL, AU, l, u, c = np.zeros(m), np.zeros(m), np.zeros(n), np.zeros(n), np.zeros(n)
+    xs, ys, zs = np.zeros(n), np.zeros(m), np.zeros(n)
+    obj = L.synth_lp_vectors(m, n, _ip(lp["rowPtr"]), _ip(lp["colIndex"]), _dp(lp["values"]), seed, vec_seed,
+                             _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(c), _dp(xs), _dp(ys), _dp(zs))
+    return dict(AL=AL, AU=AU, l=l, u=u, c=c, xs=xs, ys=ys, zs=zs, obj_star=obj)
+
+
+TOY_LP = dict(m=2, n=2, rowPtr=np.array([0, 2, 4], np.int32), colIndex=np.array([0, 1, 0, 1], np.int32),
+              values=np.array([1.0, 2.0, 3.0, 1.0]), AL=np.array([-np.inf, -np.inf]), AU=np.array([10.0, 12.0]),
+              l=np.zeros(2), u=np.full(2, np.inf), c=np.array([-3.0, -5.0]))
+"""The toy LP of every reference example (examples/cpp/example_direct_lp.cpp:14): x*=(2.8,3.6), obj=-26.4."""

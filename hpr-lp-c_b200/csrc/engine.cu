@@ -1,0 +1,923 @@
+// engine.cu -- B200-native HPR-LP engine: device setup, scaling, power iteration, the
+// Halpern/Peaceman-Rachford loop with restarts, residuals and solution collection.
+// Host control flow restates the reference driver (src/HPRLP.cu:116-311, src/main_iterate.cu)
+// exactly; every device operation is one of the hand-written kernels of kernels.cuh or the small
+// vector kernels below.  No cuSPARSE / cuBLAS / cuSOLVER anywhere; cuRAND only produces the
+// power-iteration start vector (setup), as the reference does (src/power_iteration.cu:44-52).
+#include "engine.h"
+#include "kernels.cuh"
+
+#include <curand.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace hpr {
+
+// ------------------------------------------------------------------------------------------------
+// small vector kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kVecThreads = 256;
+constexpr int kVecBlocks = 148 * 4;   // one wave of 4 CTAs per SM on B200
+
+__global__ void final_reduce_kernel(const double *partials, int n_blocks, int ns, double *out) {
+    __shared__ double sm[kMaxSlots][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int s = 0; s < ns; ++s) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) v += partials[(size_t)b * kMaxSlots + s];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[s][wid] = v;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        for (int s = 0; s < ns; ++s) {
+            double v = (lane < (int)(blockDim.x >> 5)) ? sm[s][lane] : 0.0;
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) out[s] = v;
+        }
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void vec_block_store(double (&acc)[NS], double *partials) {
+    __shared__ double scratch[kMaxSlots * (kVecThreads / 32)];
+    block_reduce_store<NS>(acc, partials, scratch);
+}
+
+// |b|^2 with b_i = max(|AL_i|,|AU_i|), +-inf -> 0 (reference conceptual_b_kernel + cublasDnrm2,
+// HPR_cuda_kernels.cu:34-43, src/scaling.cu:113-116); slot 1: |c|^2.
+__global__ void __launch_bounds__(kVecThreads) norm_bc_kernel(const double *AL, const double *AU, int m, const double *c, int n,
+                                                             double *partials) {
+    double t[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double a = AL[i], b = AU[i];
+        a = isinf(a) ? 0.0 : a;
+        b = isinf(b) ? 0.0 : b;
+        const double v = fmax(fabs(a), fabs(b));
+        t[0] += v * v;
+    }
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) t[1] += c[j] * c[j];
+    vec_block_store<2>(t, partials);
+}
+
+__global__ void __launch_bounds__(kVecThreads) sumsq_kernel(const double *v, int len, double *partials) {
+    double t[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) t[0] += v[i] * v[i];
+    vec_block_store<1>(t, partials);
+}
+
+// restart: movement norms |x_bar-x0|^2, |y_bar-y0|^2 (reference update_sigma axpby+nrm2,
+// src/main_iterate.cu:370-376) fused with do_restart's four copies (:312-322).
+__global__ void __launch_bounds__(kVecThreads) restart_kernel(const double *x_bar, double *x0, double *x, int n, const double *y_bar,
+                                                             double *y0, double *y, int m, double *partials) {
+    double t[2] = {0.0, 0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double xb = x_bar[j];
+        const double d = xb - x0[j];
+        t[0] += d * d;
+        x0[j] = xb;
+        x[j] = xb;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const double yb = y_bar[i];
+        const double d = yb - y0[i];
+        t[1] += d * d;
+        y0[i] = yb;
+        y[i] = yb;
+    }
+    vec_block_store<2>(t, partials);
+}
+
+// q = z / sqrt(<z,z> + eps)  (reference src/power_iteration.cu:62-70), <z,z> read from a device scalar.
+__global__ void power_normalize_kernel(const double *z, double *q, const double *zz, int m) {
+    const double invn = 1.0 / sqrt(zz[0] + 2.220446049250313e-16);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) q[i] = invn * z[i];
+}
+
+// |z - lambda q|^2 with lambda = <q,z> read from a device scalar (reference :85-93).
+__global__ void __launch_bounds__(kVecThreads) power_error_kernel(const double *z, const double *q, const double *lambda, int m, double *partials) {
+    const double lam = lambda[0];
+    double t[1] = {0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const double r = fma(-lam, q[i], z[i]);
+        t[0] += r * r;
+    }
+    vec_block_store<1>(t, partials);
+}
+
+__global__ void set_params_kernel(double *params, double sigma, double lambda_max) {
+    const double f = lambda_max * sigma;
+    params[0] = sigma;
+    params[1] = f;
+    params[2] = 1.0 / f;
+    params[3] = 1.0 / sigma;
+}
+
+__global__ void fill_kernel(double *v, int len, double value) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) v[i] = value;
+}
+__global__ void add_scalar_kernel(double *v, int len, double value) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) v[i] += value;
+}
+__global__ void scal_kernel(double *v, int len, double alpha) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) v[i] = alpha * v[i];
+}
+__global__ void exp_clamp_kernel(double *v, int len) {   // reference src/scaling.cu:33-38
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+        v[i] = fmin(fmax(exp(v[i]), 1e-30), 1e30);
+}
+// Row-side vector updates of one scaling stage.  CR multiplies (norm /= t, AL,AU *= t;
+// src/scaling.cu:69-80), Ruiz/PC divide (norm *= t, AL,AU /= t; :129-133).
+template <bool CR>
+__global__ void scale_row_vectors_kernel(const double *t, double *norm, double *AL, double *AU, int m) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const double f = t[i];
+        if (CR) { norm[i] = norm[i] / f; AL[i] = AL[i] * f; AU[i] = AU[i] * f; }
+        else    { norm[i] = norm[i] * f; AL[i] = AL[i] / f; AU[i] = AU[i] / f; }
+    }
+}
+// Column side: CR  norm /= t, c *= t, l,u /= t ; Ruiz/PC  norm *= t, c /= t, l,u *= t.
+template <bool CR>
+__global__ void scale_col_vectors_kernel(const double *t, double *norm, double *c, double *l, double *u, int n) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double f = t[j];
+        if (CR) { norm[j] = norm[j] / f; c[j] = c[j] * f; l[j] = l[j] / f; u[j] = u[j] / f; }
+        else    { norm[j] = norm[j] * f; c[j] = c[j] / f; l[j] = l[j] * f; u[j] = u[j] * f; }
+    }
+}
+// x = b_scale (x_bar / col_norm), z = c_scale (z_bar * col_norm), y = c_scale (y_bar / row_norm)
+// (reference collect_solution, src/utils.cu:172-189: elementwise op, then a separate scale).
+__global__ void unscale_kernel(const double *x_bar, const double *z_bar, const double *col_norm, double *xo, double *zo, int n,
+                               const double *y_bar, const double *row_norm, double *yo, int m, double bs, double cs) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double cn = col_norm[j];
+        double a = x_bar[j] / cn;
+        double b = z_bar[j] * cn;
+        xo[j] = bs * a;
+        zo[j] = cs * b;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double a = y_bar[i] / row_norm[i];
+        yo[i] = cs * a;
+    }
+}
+
+static inline int vec_grid(int len) {
+    int g = (len + kVecThreads - 1) / kVecThreads;
+    return std::max(1, std::min(g, kVecBlocks));
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static CsrView<int> view_of(const DevCsr &M) {
+    CsrView<int> v;
+    v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
+    v.item_row = M.item_row; v.n_items = M.n_items;
+    v.head_part = M.head_part; v.tail_part = M.tail_part; v.counters = M.counters;
+    return v;
+}
+
+template <class Op>
+static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
+    const CsrView<int> v = view_of(M);
+    switch (M.G) {
+        case 1:  csr_stream_kernel<Op, 1, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        case 2:  csr_stream_kernel<Op, 2, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        case 4:  csr_stream_kernel<Op, 4, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        case 8:  csr_stream_kernel<Op, 8, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        case 16: csr_stream_kernel<Op, 16, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        default: csr_stream_kernel<Op, 32, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+    }
+}
+// setup / check-iteration passes: fewer instantiations
+template <class Op>
+static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
+    const CsrView<int> v = view_of(M);
+    if (M.G <= 2)      csr_stream_kernel<Op, 1, int><<<M.n_items, kThreads, 0, st>>>(v, op);
+    else if (M.G <= 8) csr_stream_kernel<Op, 4, int><<<M.n_items, kThreads, 0, st>>>(v, op);
+    else               csr_stream_kernel<Op, 16, int><<<M.n_items, kThreads, 0, st>>>(v, op);
+}
+
+template <typename T>
+static T *dalloc(size_t count) {
+    T *p = nullptr;
+    HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    return p;
+}
+static void dfree(void *p) { if (p) cudaFree(p); }
+
+static double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// reference src/utils.cu:100-102
+static int step_of(int iter) {
+    return std::max(10, static_cast<int>(pow(10, floor(log10((double)iter))) / 10));
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup
+// ------------------------------------------------------------------------------------------------
+void csr_transpose_host(int rows, int cols, int nnz, const int *rp, const int *ci, const double *v,
+                        int *trp, int *tci, double *tv) {
+    // Stable counting sort by column: entries of a transposed row keep the original row order,
+    // i.e. the same entry order as the reference's CSR_transpose_host (src/utils.cu:203-232).
+    std::vector<int> cursor((size_t)cols + 1, 0);
+    for (int k = 0; k < nnz; ++k) cursor[(size_t)ci[k] + 1]++;
+    for (int j = 0; j < cols; ++j) cursor[j + 1] += cursor[j];
+    for (int j = 0; j <= cols; ++j) trp[j] = cursor[j];
+    for (int i = 0; i < rows; ++i)
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int pos = cursor[ci[k]]++;
+            tci[pos] = i;
+            tv[pos] = v[k];
+        }
+}
+
+static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
+    M.rows = rows; M.cols = cols; M.nnz = nnz;
+    M.n_items = (int)((nnz + kChunk - 1) / kChunk);
+    if (M.n_items < 1) M.n_items = 1;
+    const size_t padded = (size_t)M.n_items * kChunk;
+    M.rowPtr = dalloc<int>((size_t)rows + 1);
+    M.col = dalloc<int>(padded);
+    M.val = dalloc<double>(padded);
+    M.item_row = dalloc<int>((size_t)M.n_items + 1);
+    M.head_part = dalloc<double>((size_t)M.n_items * 2);
+    M.tail_part = dalloc<double>((size_t)M.n_items * 2);
+    M.counters = dalloc<unsigned>((size_t)M.n_items);
+}
+static void free_matrix(DevCsr &M) {
+    dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
+    dfree(M.head_part); dfree(M.tail_part); dfree(M.counters);
+    M = DevCsr();
+}
+
+static int pick_lanes(double mean_len, const char *env_name) {
+    if (const char *e = getenv(env_name)) {
+        const int g = atoi(e);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
+    }
+    // lanes per row ~ mean_len / 6, power of two (measured row-length statistic of this matrix)
+    if (mean_len < 6.0) return 1;
+    if (mean_len < 12.0) return 2;
+    if (mean_len < 24.0) return 4;
+    if (mean_len < 48.0) return 8;
+    if (mean_len < 96.0) return 16;
+    return 32;
+}
+
+void Engine::finish_matrix(DevCsr &M) {
+    const int threads = 256;
+    build_item_rows_kernel<int><<<(M.n_items + 1 + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.n_items, M.item_row);
+    launches++;
+    M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
+}
+
+void Engine::alloc_common() {
+    x = dalloc<double>(n); x0 = dalloc<double>(n); x_hat = dalloc<double>(n); x_bar = dalloc<double>(n);
+    z_bar = dalloc<double>(n); x_tmp = dalloc<double>(n); wn = dalloc<double>(n);
+    y = dalloc<double>(m); y0 = dalloc<double>(m); y_bar = dalloc<double>(m); y_obj = dalloc<double>(m);
+    y_tmp = dalloc<double>(m); wm = dalloc<double>(m); wm2 = dalloc<double>(m);
+    row_norm = dalloc<double>(m); col_norm = dalloc<double>(n);
+    d_params = dalloc<double>(4);
+    d_k = dalloc<int>(2);
+    partial_blocks = std::max(std::max(A.n_items, AT.n_items), kVecBlocks);
+    d_partials = dalloc<double>((size_t)partial_blocks * kMaxSlots);
+    d_scal = dalloc<double>(16);
+    HPR_CUDA_CHECK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
+    HPR_CUDA_CHECK(cudaMallocHost(&h_params, 4 * sizeof(double)));
+    A.G = pick_lanes(A.mean_len, "HPRLP_LANES_A");
+    AT.G = pick_lanes(AT.mean_len, "HPRLP_LANES_AT");
+}
+
+void Engine::upload(const LP_info_cpu *lp, int dev) {
+    device = dev;
+    HPR_CUDA_CHECK(cudaSetDevice(device));
+    HPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    m = lp->m; n = lp->n; nnz = lp->A->numElements;
+    obj_constant = lp->obj_constant;
+    alloc_matrix(A, m, n, nnz);
+    alloc_matrix(AT, n, m, nnz);
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.rowPtr, lp->A->rowPtr, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.col, lp->A->colIndex, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.val, lp->A->value, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+    {
+        std::vector<int> trp((size_t)n + 1), tci((size_t)nnz);
+        std::vector<double> tv((size_t)nnz);
+        csr_transpose_host(m, n, (int)nnz, lp->A->rowPtr, lp->A->colIndex, lp->A->value, trp.data(), tci.data(), tv.data());
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.rowPtr, trp.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.col, tci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.val, tv.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    AL = dalloc<double>(m); AU = dalloc<double>(m); c = dalloc<double>(n); l = dalloc<double>(n); u = dalloc<double>(n);
+    HPR_CUDA_CHECK(cudaMemcpyAsync(AL, lp->AL, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(AU, lp->AU, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(c, lp->c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(l, lp->l, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(u, lp->u, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    finish_matrix(A);
+    finish_matrix(AT);
+    alloc_common();
+    HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+Engine::~Engine() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
+    graphs_.clear();
+    free_matrix(A); free_matrix(AT);
+    dfree(AL); dfree(AU); dfree(c); dfree(l); dfree(u);
+    dfree(row_norm); dfree(col_norm);
+    dfree(x); dfree(x0); dfree(x_hat); dfree(x_bar); dfree(z_bar); dfree(x_tmp); dfree(wn);
+    dfree(y); dfree(y0); dfree(y_bar); dfree(y_obj); dfree(y_tmp); dfree(wm); dfree(wm2);
+    dfree(d_params); dfree(d_k); dfree(d_partials); dfree(d_scal);
+    if (h_scal) cudaFreeHost(h_scal);
+    if (h_params) cudaFreeHost(h_params);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::fetch_scalars(int count) {
+    HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+    HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// scaling (reference src/scaling.cu:88-216)
+// ------------------------------------------------------------------------------------------------
+void Engine::scale(const HPRLP_parameters *p) {
+    double *t1 = wm, *t2 = wn;
+    const int gm = vec_grid(m), gn = vec_grid(n);
+    fill_kernel<<<gm, kVecThreads, 0, stream>>>(row_norm, m, 1.0);
+    fill_kernel<<<gn, kVecThreads, 0, stream>>>(col_norm, n, 1.0);
+    launches += 2;
+
+    auto norms_bc = [&](double *nb, double *nc) {
+        norm_bc_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(AL, AU, m, c, n, d_partials);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 2, d_scal);
+        launches += 2;
+        fetch_scalars(2);
+        *nb = sqrt(h_scal[0]);
+        *nc = sqrt(h_scal[1]);
+    };
+    double nb, nc;
+    norms_bc(&nb, &nc);
+    norm_b_org = 1.0 + nb;
+    norm_c_org = 1.0 + nc;
+
+    const CsrView<int> vA = view_of(A), vAT = view_of(AT);
+    if (p->use_CR_scaling) {
+        // 20 alternating log-mean sweeps from zero (src/scaling.cu:40-64)
+        fill_kernel<<<gm, kVecThreads, 0, stream>>>(t1, m, 0.0);
+        fill_kernel<<<gn, kVecThreads, 0, stream>>>(t2, n, 0.0);
+        launches += 2;
+        for (int it = 0; it < 20; ++it) {
+            CurtisReidOp oa; oa.other = t2; oa.out = t1;
+            launch_stream(A, oa, stream);
+            CurtisReidOp ob; ob.other = t1; ob.out = t2;
+            launch_stream(AT, ob, stream);
+            launches += 2;
+        }
+        exp_clamp_kernel<<<gm, kVecThreads, 0, stream>>>(t1, m);
+        exp_clamp_kernel<<<gn, kVecThreads, 0, stream>>>(t2, n);
+        scale_values_kernel<false, true, int><<<A.n_items, kThreads, 0, stream>>>(vA, A.val, t1, t2);
+        scale_values_kernel<false, false, int><<<AT.n_items, kThreads, 0, stream>>>(vAT, AT.val, t2, t1);
+        scale_row_vectors_kernel<true><<<gm, kVecThreads, 0, stream>>>(t1, row_norm, AL, AU, m);
+        scale_col_vectors_kernel<true><<<gn, kVecThreads, 0, stream>>>(t2, col_norm, c, l, u, n);
+        launches += 6;
+    }
+    const int ruiz_rounds = p->use_Ruiz_scaling ? 10 : 0;
+    const int rounds = ruiz_rounds + (p->use_Pock_Chambolle_scaling ? 1 : 0);
+    for (int it = 0; it < rounds; ++it) {
+        // both statistics are taken from the matrix before either factor is applied (:127-144)
+        if (it < ruiz_rounds) {
+            RowNormOp<true> oa; oa.out = t1; launch_stream(A, oa, stream);
+            RowNormOp<true> ob; ob.out = t2; launch_stream(AT, ob, stream);
+        } else {
+            RowNormOp<false> oa; oa.out = t1; launch_stream(A, oa, stream);
+            RowNormOp<false> ob; ob.out = t2; launch_stream(AT, ob, stream);
+        }
+        scale_values_kernel<true, true, int><<<A.n_items, kThreads, 0, stream>>>(vA, A.val, t1, t2);
+        scale_values_kernel<true, false, int><<<AT.n_items, kThreads, 0, stream>>>(vAT, AT.val, t2, t1);
+        scale_row_vectors_kernel<false><<<gm, kVecThreads, 0, stream>>>(t1, row_norm, AL, AU, m);
+        scale_col_vectors_kernel<false><<<gn, kVecThreads, 0, stream>>>(t2, col_norm, c, l, u, n);
+        launches += 6;
+    }
+    if (p->use_bc_scaling) {
+        norms_bc(&nb, &nc);
+        b_scale = 1.0 + nb;
+        c_scale = 1.0 + nc;
+        const double bs = 1.0 / b_scale, cs = 1.0 / c_scale;
+        scal_kernel<<<gm, kVecThreads, 0, stream>>>(AU, m, bs);
+        scal_kernel<<<gm, kVecThreads, 0, stream>>>(AL, m, bs);
+        scal_kernel<<<gn, kVecThreads, 0, stream>>>(l, n, bs);
+        scal_kernel<<<gn, kVecThreads, 0, stream>>>(u, n, bs);
+        scal_kernel<<<gn, kVecThreads, 0, stream>>>(c, n, cs);
+        launches += 5;
+    } else {
+        b_scale = 1.0;
+        c_scale = 1.0;
+    }
+    norms_bc(&nb, &nc);
+    norm_b = nb;
+    norm_c = nc;
+    HPR_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// power iteration (reference src/power_iteration.cu:20-119)
+// ------------------------------------------------------------------------------------------------
+void Engine::power_start_vector(double *d_z) {
+    // cuRAND XORWOW (CURAND_RNG_PSEUDO_DEFAULT), seed 1, N(0,1), then + 1e-8.  For odd m the reference's
+    // unchecked curandGenerateNormalDouble fails with LENGTH_NOT_MULTIPLE and leaves z = 0 (its Ax
+    // buffer after the warm-up SpMV with x_bar = 0, src/preprocess.cu:153-156) => z = 1e-8 * ones.
+    HPR_CUDA_CHECK(cudaMemsetAsync(d_z, 0, sizeof(double) * m, stream));
+    if ((m % 2) == 0) {
+        curandGenerator_t gen = nullptr;
+        if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
+            throw std::runtime_error("curandCreateGenerator failed");
+        curandSetStream(gen, stream);
+        curandSetPseudoRandomGeneratorSeed(gen, 1ULL);
+        curandGenerateNormalDouble(gen, d_z, (size_t)m, 0.0, 1.0);
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        curandDestroyGenerator(gen);
+    }
+    add_scalar_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(d_z, m, 1e-8);
+    launches++;
+}
+
+double Engine::power_iteration(int max_iter, double tol, const double *host_z0, int *iters_out) {
+    double *z = wm, *q = wm2, *atq = wn;
+    if (host_z0) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(z, host_z0, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    } else {
+        power_start_vector(z);
+    }
+    // d_scal[0] = <z,z>, d_scal[1] = <q,z>, d_scal[2] = |z - lambda q|^2
+    sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, m, d_partials);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal);
+    launches += 2;
+    double lambda = 1.0;
+    int it;
+    for (it = 1; it <= max_iter; ++it) {
+        power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
+        SpmvOp<false> o1; o1.g = q; o1.out = atq; o1.q = nullptr; o1.partials = nullptr;
+        launch_stream(AT, o1, stream);
+        SpmvOp<true> o2; o2.g = atq; o2.out = z; o2.q = q; o2.partials = d_partials;
+        launch_stream(A, o2, stream);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 2, d_scal);
+        launches += 4;
+        if (it % 10 == 0) {
+            power_error_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, q, d_scal + 1, m, d_partials);
+            final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
+            launches += 2;
+            fetch_scalars(3);
+            lambda = h_scal[1];
+            if (sqrt(h_scal[2]) < tol) break;
+        }
+    }
+    if (it > max_iter) {
+        it = max_iter;
+        printf("Power iteration did not converge within the specified tolerance.\nMax iter: %d, Error: %.2e\n", max_iter,
+               sqrt(h_scal[2]));
+    }
+    if (iters_out) *iters_out = it;
+    HPR_CUDA_CHECK(cudaGetLastError());
+    return lambda;
+}
+
+// ------------------------------------------------------------------------------------------------
+// iteration building blocks
+// ------------------------------------------------------------------------------------------------
+void Engine::init_iterates() {
+    for (double *v : {x, x0, x_hat, x_bar, z_bar, x_tmp}) HPR_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, stream));
+    for (double *v : {y, y0, y_bar, y_obj, y_tmp}) HPR_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * m, stream));
+    reset_halpern_counter();
+    upload_params();
+}
+
+void Engine::upload_params() {   // reference reset_/upload_halpern_*_params, src/main_iterate.cu:17-66
+    set_params_kernel<<<1, 1, 0, stream>>>(d_params, sigma, lambda_max);
+    launches++;
+}
+
+void Engine::reset_halpern_counter() { HPR_CUDA_CHECK(cudaMemsetAsync(d_k, 0, 2 * sizeof(int), stream)); }
+
+void Engine::launch_iteration(bool check) {
+    if (check) {
+        XPhaseOp<true> ox;
+        ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+        ox.x_bar = x_bar; ox.z_bar = z_bar; ox.x_tmp = x_tmp; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
+        launch_stream_hot(AT, ox, stream);
+        YPhaseOp<true> oy;
+        oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+        oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+        launch_stream_hot(A, oy, stream);
+    } else {
+        XPhaseOp<false> ox;
+        ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+        ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
+        launch_stream_hot(AT, ox, stream);
+        YPhaseOp<false> oy;
+        oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+        oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+        launch_stream_hot(A, oy, stream);
+    }
+    launches += 2;
+}
+
+// `count` normal iterations.  Kernel arguments are immutable (sigma and the Halpern counter live in
+// device memory), so a captured graph of L iterations is replayable (the reference captures one
+// iteration, src/HPRLP.cu:99-114); graphs are cached per length.
+void Engine::run_normal(int count) {
+    static const bool no_graph = getenv("HPRLP_NO_GRAPH") != nullptr;
+    while (count > 0) {
+        int len = std::min(count, 128);
+        if (no_graph || len < 2) {
+            for (int i = 0; i < len; ++i) launch_iteration(false);
+        } else {
+            auto it = graphs_.find(len);
+            if (it == graphs_.end()) {
+                cudaGraph_t g = nullptr;
+                cudaGraphExec_t ge = nullptr;
+                HPR_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                const long long before = launches;
+                for (int i = 0; i < len; ++i) launch_iteration(false);
+                launches = before;
+                HPR_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+                HPR_CUDA_CHECK(cudaGraphInstantiate(&ge, g, nullptr, nullptr, 0));
+                cudaGraphDestroy(g);
+                it = graphs_.emplace(len, ge).first;
+            }
+            HPR_CUDA_CHECK(cudaGraphLaunch(it->second, stream));
+            launches += 2LL * len;
+        }
+        count -= len;
+    }
+}
+
+// reference compute_residuals, src/main_iterate.cu:229-309 -- two fused passes, one D2H of 9 scalars.
+void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, RestartState *rs) {
+    auto fill_dual = [&](auto &o) {
+        o.y_bar = y_bar; o.c = c; o.z_bar = z_bar; o.x_bar = x_bar; o.x_tmp = x_tmp; o.col_norm = col_norm;
+        o.l = l; o.u = u; o.partials = d_partials;
+    };
+    if (iter == 0) { ResidualDualOp<false, true> o; fill_dual(o); launch_stream(AT, o, stream); }
+    else if (compute_gap) { ResidualDualOp<true, false> o; fill_dual(o); launch_stream(AT, o, stream); }
+    else { ResidualDualOp<false, false> o; fill_dual(o); launch_stream(AT, o, stream); }
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, AT.n_items, 5, d_scal);
+    auto fill_primal = [&](auto &o) {
+        o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
+        o.y_bar = y_bar; o.y_tmp = y_tmp; o.partials = d_partials;
+    };
+    if (compute_gap) { ResidualPrimalOp<true> o; fill_primal(o); launch_stream(A, o, stream); }
+    else { ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream); }
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 4, d_scal + 5);
+    launches += 4;
+    fetch_scalars(9);
+    HPR_CUDA_CHECK(cudaGetLastError());
+
+    const double obj_scale = b_scale * c_scale;
+    res->primal_obj = obj_scale * h_scal[1] + obj_constant;
+    res->dual_obj = obj_scale * (h_scal[6] + h_scal[2]) + obj_constant;
+    res->rel_gap = std::abs(res->primal_obj - res->dual_obj) / (1.0 + std::abs(res->primal_obj) + std::abs(res->dual_obj));
+    res->err_Rd = c_scale * sqrt(h_scal[0]) / norm_c_org;
+    res->err_Rp = b_scale * sqrt(h_scal[5]) / norm_b_org;
+    if (iter == 0) res->err_Rp = std::max(res->err_Rp, b_scale * sqrt(h_scal[4]));
+    res->kkt = std::max(std::max(res->err_Rd, res->err_Rp), res->rel_gap);
+
+    if (compute_gap && rs != nullptr) {
+        const double dot_prod = 2.0 * h_scal[7];
+        const double dy2 = h_scal[8];
+        const double dx2 = h_scal[3];
+        double wnorm = sigma * (lambda_max * dy2) + dx2 / sigma + dot_prod;
+        if (wnorm < 0) {
+            printf("The estimated maximum eigenvalue is too small! Current value is %g\n", lambda_max);
+            lambda_max = -(dot_prod + dx2 / sigma) / (sigma * dy2) * 1.05;
+            printf("The new estimated maximum eigenvalue is %g\n", lambda_max);
+            wnorm = sqrt(-(dot_prod + dx2 / sigma) * 0.05);
+        } else {
+            wnorm = sqrt(wnorm);
+        }
+        rs->current_gap = wnorm;
+    }
+}
+
+// reference compute_weighted_norm, src/main_iterate.cu:486-515
+double Engine::weighted_norm_after_restart() {
+    WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
+    launch_stream(A, o, stream);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 2, d_scal);
+    sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp, n, d_partials);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
+    launches += 4;
+    fetch_scalars(3);
+    const double dot_prod = 2.0 * h_scal[0];
+    const double dy2 = h_scal[1];
+    const double dx2 = h_scal[2];
+    double wnorm = sigma * (lambda_max * dy2) + dx2 / sigma + dot_prod;
+    if (wnorm < 0) {
+        printf("The estimated value of lambda_max is too small!\n");
+        lambda_max = -(dot_prod + dx2 / sigma) / (sigma * dy2) * 1.05;
+        wnorm = sqrt(-(dot_prod + dx2 / sigma) * 0.05);
+    } else {
+        wnorm = sqrt(wnorm);
+    }
+    return wnorm;
+}
+
+// reference update_sigma + do_restart + upload_halpern_restart_params,
+// src/main_iterate.cu:367-404, 312-322, 54-66
+void Engine::restart_and_sigma(RestartState *rs, const Residuals &res) {
+    restart_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_bar, x0, x, n, y_bar, y0, y, m, d_partials);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 2, d_scal);
+    launches += 2;
+    fetch_scalars(2);
+    const double primal_move = sqrt(h_scal[0]);
+    const double dual_move = sqrt(h_scal[1]);
+    if (primal_move > 1e-16 && dual_move > 1e-16 && primal_move < 1e12 && dual_move < 1e12) {
+        const double pm_over_dm = primal_move / dual_move;
+        const double sqrt_lambda = sqrt(lambda_max);
+        const double ratio = pm_over_dm / sqrt_lambda;
+        const double fact = std::exp(-0.05 * (rs->current_gap / rs->best_gap));
+        const double temp1 = std::max(std::min(res.err_Rd, res.err_Rp), std::min(res.rel_gap, rs->current_gap));
+        const double sigma_cand = std::exp(fact * std::log(ratio) + (1 - fact) * std::log(rs->best_sigma));
+        double kappa;
+        if (temp1 > 9e-10) {
+            kappa = 1.0;
+        } else if (temp1 > 5e-10) {
+            const double ratio_infeas = res.err_Rd / res.err_Rp;
+            kappa = std::max(std::min(std::sqrt(ratio_infeas), 100.0), 1e-2);
+        } else {
+            const double ratio_infeas = res.err_Rd / res.err_Rp;
+            kappa = std::max(std::min(ratio_infeas, 100.0), 1e-2);
+        }
+        sigma = kappa * sigma_cand;
+    } else {
+        sigma = 1.0;
+    }
+    rs->inner = 0;
+    rs->times += 1;
+    rs->save_gap = std::numeric_limits<double>::infinity();
+    reset_halpern_counter();
+}
+
+void Engine::collect_solution(double *hx, double *hy, double *hz) {
+    // unscale into scratch (wn, x_hat reused as z scratch is NOT allowed: x_hat is live) -> use wn/wm + x_tmp copy
+    double *xo = wn, *yo = wm;
+    double *zo = dalloc<double>(n);
+    unscale_kernel<<<vec_grid(std::max(m, n)), kVecThreads, 0, stream>>>(x_bar, z_bar, col_norm, xo, zo, n, y_bar, row_norm, yo, m,
+                                                                         b_scale, c_scale);
+    launches++;
+    HPR_CUDA_CHECK(cudaMemcpyAsync(hx, xo, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(hy, yo, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(hz, zo, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+    HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    dfree(zo);
+}
+
+double Engine::time_phase_ms(int which, int reps) {
+    cudaEvent_t e0, e1;
+    HPR_CUDA_CHECK(cudaEventCreate(&e0));
+    HPR_CUDA_CHECK(cudaEventCreate(&e1));
+    auto one = [&]() {
+        if (which == 0) {
+            XPhaseOp<false> ox;
+            ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+            ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
+            launch_stream_hot(AT, ox, stream);
+        } else {
+            YPhaseOp<false> oy;
+            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+            launch_stream_hot(A, oy, stream);
+        }
+        launches++;
+    };
+    one();
+    HPR_CUDA_CHECK(cudaEventRecord(e0, stream));
+    for (int i = 0; i < reps; ++i) one();
+    HPR_CUDA_CHECK(cudaEventRecord(e1, stream));
+    HPR_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HPR_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)ms / reps;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the driver (reference HPRLP_main_solve from the start of the timed region, src/HPRLP.cu:150-311)
+// ------------------------------------------------------------------------------------------------
+static void check_restart(RestartState *r, int iter, int check_iter, double sigma) {
+    // reference src/main_iterate.cu:324-364
+    r->restart_flag = 0;
+    if (r->first_restart) {
+        if (iter == check_iter) {
+            r->first_restart = false;
+            r->restart_flag = 1;
+            r->best_gap = r->current_gap;
+            r->best_sigma = sigma;
+        }
+    } else if (iter % check_iter == 0) {
+        if (r->current_gap < 0) {
+            r->current_gap = 1e-6;
+            printf("current_gap < 0\n");
+        }
+        if (r->current_gap <= 0.2 * r->last_gap) { r->sufficient += 1; r->restart_flag = 1; }
+        if ((r->current_gap <= 0.6 * r->last_gap) && (r->current_gap > 1.00 * r->save_gap)) { r->necessary += 1; r->restart_flag = 2; }
+        if (r->inner >= 0.2 * iter) { r->long_ += 1; r->restart_flag = 3; }
+        if (r->best_gap > r->current_gap) { r->best_gap = r->current_gap; r->best_sigma = sigma; }
+        r->save_gap = r->current_gap;
+    }
+}
+
+void Engine::solve_begin(const HPRLP_parameters *param, SolveHooks *hooks) {
+    LoopState &L = loop;
+    L = LoopState();
+    L.t_start_alg = now_seconds();
+    const bool quiet = hooks->quiet;
+    // lambda_max(A A^T) * 1.01 (reference compute_maximum_eigenvalue, src/HPRLP.cu:81-97)
+    {
+        const double t0 = now_seconds();
+        int piters = 0;
+        lambda_max = power_iteration(5000, 1e-4, hooks->power_z0, &piters) * 1.01;
+        hooks->power_iters = piters;
+        hooks->power_seconds = now_seconds() - t0;
+        if (!quiet) printf("ESTIMATING MAXIMUM EIGENVALUE time = %.2f seconds\n", hooks->power_seconds);
+    }
+    sigma = (norm_b > 1e-8 && norm_c > 1e-8) ? norm_b / norm_c : 1.0;
+    L.rs.best_sigma = sigma;
+    init_iterates();
+    L.output.residuals = 0; L.output.primal_obj = 0; L.output.gap = 0;
+    std::memset(L.output.status, 0, sizeof(L.output.status));
+    if (!quiet) {
+        printf(" iter     errRp        errRd         p_obj            d_obj          gap         sigma       time\n");
+        fflush(stdout);
+    }
+    L.uploaded_sigma = sigma;
+    L.uploaded_lambda = lambda_max;
+    L.iter = 0;
+    (void)param;
+}
+
+// Advances the driver.  Returns true when a stopping status was reached (L.output is final), false
+// when paused at iteration index `pause_at` (>0; bench/step-wise use; pause indices should be
+// multiples of step() so that they coincide with the reference's own residual iterations).
+bool Engine::solve_advance(const HPRLP_parameters *param, SolveHooks *hooks, int pause_at) {
+    LoopState &L = loop;
+    RestartState &rs = L.rs;
+    Residuals &res = L.res;
+    HPRLP_results &output = L.output;
+    const bool quiet = hooks->quiet;
+    const double t_start_alg = L.t_start_alg;
+    const int check_iter = std::max(param->check_iter, 1);
+    bool first_pass = true;
+    for (;;) {
+        int &iter = L.iter;
+        if (pause_at > 0 && iter >= pause_at && !first_pass) return false;
+        first_pass = false;
+        // every index visited here is "eventful": periodic, print or max_iter (see next_event below)
+        const bool periodic = (iter % check_iter == 0);
+        const bool compute_gap = periodic && iter > 0;
+        compute_residuals(iter, compute_gap, &res, &rs);
+
+        const double elapsed = now_seconds() - t_start_alg;
+        const char *status = "CONTINUE";   // reference check_stopping, src/main_iterate.cu:406-420
+        if (res.kkt < param->stop_tol) status = "OPTIMAL";
+        else if (iter >= param->max_iter) status = "ITER_LIMIT";
+        else if (elapsed > param->time_limit) status = "TIME_LIMIT";
+
+        if (periodic) check_restart(&rs, iter, check_iter, sigma);
+        else rs.restart_flag = 0;
+
+        // reference print_flag, src/HPRLP.cu:184-186,207
+        const bool print_flag = (iter % step_of(iter) == 0) || (iter == param->max_iter) || (elapsed > param->time_limit);
+        if (!quiet && (print_flag || std::strcmp(status, "CONTINUE") != 0)) {
+            printf("%5d    %.2e    %.2e    %+.6e    %+.6e    %.2e    %.2e      %.2f\n", iter, res.err_Rp, res.err_Rd,
+                   res.primal_obj, res.dual_obj, res.rel_gap, sigma, now_seconds() - t_start_alg);
+            fflush(stdout);
+        }
+        if (L.first_4 && res.kkt < 1e-4) {
+            output.iter4 = iter; output.time4 = now_seconds() - t_start_alg; L.first_4 = false;
+            if (!quiet) printf("Residual < 1e-4 at iter = %d\n", iter);
+        }
+        if (L.first_6 && res.kkt < 1e-6) {
+            output.iter6 = iter; output.time6 = now_seconds() - t_start_alg; L.first_6 = false;
+            if (!quiet) printf("Residual < 1e-6 at iter = %d\n", iter);
+        }
+        if (L.first_8 && res.kkt < 1e-8) {
+            output.iter8 = iter; output.time8 = now_seconds() - t_start_alg; L.first_8 = false;
+            if (!quiet) printf("Residual < 1e-8 at iter = %d\n", iter);
+        }
+
+        if (std::strcmp(status, "CONTINUE") != 0) {
+            std::strncpy(output.status, status, sizeof(output.status) - 1);
+            output.iter = iter;
+            output.gap = res.rel_gap;
+            output.residuals = res.kkt;
+            output.primal_obj = res.primal_obj;
+            output.time = now_seconds() - t_start_alg;
+            output.time4 = (output.time4 == 0.0) ? output.time : output.time4;
+            output.time6 = (output.time6 == 0.0) ? output.time : output.time6;
+            output.time8 = (output.time8 == 0.0) ? output.time : output.time8;
+            output.iter4 = (output.iter4 == 0) ? output.iter : output.iter4;
+            output.iter6 = (output.iter6 == 0) ? output.iter : output.iter6;
+            output.iter8 = (output.iter8 == 0) ? output.iter : output.iter8;
+            output.x = static_cast<double *>(std::malloc(sizeof(double) * n));
+            output.y = static_cast<double *>(std::malloc(sizeof(double) * m));
+            output.z = static_cast<double *>(std::malloc(sizeof(double) * n));
+            collect_solution(output.x, output.y, output.z);
+            if (!quiet) {
+                printf("\n=== Solution Summary ===\nStatus: %s\nIterations: %d\nTime: %.2f seconds\n", output.status, output.iter,
+                       output.time);
+                printf("Primal Objective: %.12e\nResidual: %.12e\n\n", output.primal_obj, output.residuals);
+                fflush(stdout);
+            }
+            return true;
+        }
+
+        const bool restart = rs.restart_flag > 0;
+        if (restart) restart_and_sigma(&rs, res);
+        if (sigma != L.uploaded_sigma || lambda_max != L.uploaded_lambda) {
+            upload_params();
+            L.uploaded_sigma = sigma;
+            L.uploaded_lambda = lambda_max;
+        }
+
+        // next eventful index: next multiple of check_iter, next multiple of step(), max_iter, or the pause
+        int next_event;
+        {
+            const long long nper = ((long long)iter / check_iter + 1) * check_iter;
+            const long long i1 = (long long)iter + 1;
+            const long long st = step_of((int)std::min<long long>(i1, INT32_MAX));
+            const long long nprint = ((i1 + st - 1) / st) * st;
+            long long ne = std::min(nper, nprint);
+            if ((long long)param->max_iter > iter) ne = std::min(ne, (long long)param->max_iter);
+            if (pause_at > iter) ne = std::min(ne, (long long)pause_at);
+            next_event = (int)std::min<long long>(ne, INT32_MAX);
+        }
+        // iterations iter .. next_event-1: the last one is a check iteration when the reference's
+        // (iter+1)%check_iter==0 || (iter+1)%step(iter+1)==0 holds (src/HPRLP.cu:295-296) -- true for every
+        // eventful index except a max_iter that is not a multiple of step (quirk: stale bars at ITER_LIMIT).
+        const int count = next_event - iter;
+        const bool last_is_check = (next_event % check_iter == 0) || (next_event % step_of(next_event) == 0);
+        int done = 0;
+        if (restart) {
+            launch_iteration(true);
+            done = 1;
+            rs.last_gap = weighted_norm_after_restart();
+            if (lambda_max != L.uploaded_lambda) { upload_params(); L.uploaded_lambda = lambda_max; }
+        }
+        const int tail_check = (last_is_check && count - done >= 1) ? 1 : 0;
+        run_normal(count - done - tail_check);
+        if (tail_check) launch_iteration(true);
+        rs.inner += count;
+        iter = next_event;
+
+        for (int t = 0; t < hooks->n_trace; ++t) {
+            if (hooks->trace_iters[t] == iter && (last_is_check || (restart && count == 1))) {
+                collect_solution(hooks->trace_x + (size_t)t * n, hooks->trace_y + (size_t)t * m, hooks->trace_z + (size_t)t * n);
+            }
+        }
+    }
+}
+
+void Engine::fill_hooks(SolveHooks *hooks) {
+    hooks->lambda_max = lambda_max;
+    hooks->sigma = sigma;
+    hooks->restarts = loop.rs.times;
+    hooks->kernel_launches = launches;
+    hooks->scal[0] = b_scale; hooks->scal[1] = c_scale; hooks->scal[2] = norm_b; hooks->scal[3] = norm_c;
+    hooks->scal[4] = norm_b_org; hooks->scal[5] = norm_c_org;
+}
+
+HPRLP_results Engine::solve(const HPRLP_parameters *param, SolveHooks *hooks) {
+    SolveHooks local;
+    if (!hooks) hooks = &local;
+    cudaEvent_t ev0, ev1;
+    HPR_CUDA_CHECK(cudaEventCreate(&ev0));
+    HPR_CUDA_CHECK(cudaEventCreate(&ev1));
+    solve_begin(param, hooks);
+    HPR_CUDA_CHECK(cudaEventRecord(ev0, stream));
+    solve_advance(param, hooks, -1);
+    HPR_CUDA_CHECK(cudaEventRecord(ev1, stream));
+    HPR_CUDA_CHECK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    hooks->loop_device_ms = ms;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    fill_hooks(hooks);
+    return loop.output;
+}
+
+}  // namespace hpr

@@ -1,0 +1,126 @@
+"""CPU: host model layer (create_model_from_arrays / create_model_from_mps / CSC conversion /
+transpose order).  When the reference's own build is present (oracle/_ref) the LP_info_cpu arrays
+are compared bit-exactly against it ("MPS parsing, CSR/CSC construction ... bit-exact")."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+GOLD = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
+
+def _rand_csr(rng, m, n, density, empty_rows=()):
+    A = sp.random(m, n, density=density, random_state=rng, format="csr", dtype=np.float64)
+    A.data[:] = rng.uniform(-2, 2, A.nnz)
+    A = A.tolil()
+    for r in empty_rows:
+        A.rows[r] = []
+        A.data[r] = []
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def test_toy_mps_parses_to_known_model(engine):
+    model = engine.create_model_from_mps(GOLD / "model.mps")
+    assert model
+    a = engine.model_arrays(model)
+    engine.free_model(model)
+    assert (a["m"], a["n"], a["nnz"]) == (2, 2, 4)
+    assert a["rowPtr"].tolist() == [0, 2, 4] and a["colIndex"].tolist() == [0, 1, 0, 1]
+    assert a["values"].tolist() == [1.0, 2.0, 3.0, 1.0]
+    assert np.all(np.isneginf(a["AL"])) and a["AU"].tolist() == [10.0, 12.0]
+    assert a["l"].tolist() == [0.0, 0.0] and np.all(np.isposinf(a["u"])) and a["c"].tolist() == [-3.0, -5.0]
+    assert a["obj_constant"] == 0.0
+
+
+def test_tricky_mps_semantics(engine):
+    model = engine.create_model_from_mps(GOLD / "tricky.mps")
+    assert model
+    a = engine.model_arrays(model)
+    engine.free_model(model)
+    assert (a["m"], a["n"]) == (5, 5)
+    dense = sp.csr_matrix((a["values"], a["colIndex"], a["rowPtr"]), shape=(5, 5)).toarray()
+    want = np.array([[2.0, 1.0, 0, 0, 0], [-1.0, 0, 1.0, 2.5, 0], [0, 3.0, 1.0, 0, 0], [0, -4.5, 0, 1.0, 0],
+                     [0, 0, 0.5, -1.0, 7.0]])
+    assert np.array_equal(dense, want)
+    assert a["c"].tolist() == [1.5, -2.25, 0.0, 0.125, 0.0]
+    assert a["obj_constant"] == 3.5               # RHS on the objective row: c0 = -(-3.5)
+    # e1: rhs 4, range +2 -> [4,6]; l1: rhs 6, |range| 3 -> [3,6]; g1: rhs 1, |range| 1.5 -> [1,2.5];
+    # e2: rhs -2, range -0.5 -> [-2.5,-2]; g2: rhs from the rim set "rhs2" ignored -> [0, inf)
+    assert a["AL"].tolist() == [4.0, 3.0, 1.0, -2.5, 0.0]
+    assert a["AU"][:4].tolist() == [6.0, 6.0, 2.5, -2.0] and np.isposinf(a["AU"][4])
+    # x1: UP -1 with no lower -> l=-inf; x2: MI -> (-inf, inf); x3: integer-marked default [0,1];
+    # x4: FX 2.5; x5: FR, the rim bound set "bnd2" ignored
+    assert np.isneginf(a["l"][0]) and a["u"][0] == -1.0
+    assert np.isneginf(a["l"][1]) and np.isposinf(a["u"][1])
+    assert (a["l"][2], a["u"][2]) == (0.0, 1.0)
+    assert (a["l"][3], a["u"][3]) == (2.5, 2.5)
+    assert np.isneginf(a["l"][4]) and np.isposinf(a["u"][4])
+
+
+@pytest.mark.parametrize("name", ["model.mps", "tricky.mps", "dup.mps"])
+def test_mps_bit_exact_vs_reference_build(engine, reference, name):
+    mine = engine.create_model_from_mps(GOLD / name)
+    ref = reference.create_model_from_mps(GOLD / name)
+    assert mine and ref
+    a, b = engine.model_arrays(mine), reference.model_arrays(ref)
+    engine.free_model(mine); reference.free_model(ref)
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
+
+
+def test_gz_mps(engine, tmp_path):
+    import gzip
+    p = tmp_path / "model.mps.gz"
+    p.write_bytes(gzip.compress((GOLD / "model.mps").read_bytes()))
+    model = engine.create_model_from_mps(p)
+    assert model
+    assert engine.model_arrays(model)["values"].tolist() == [1.0, 2.0, 3.0, 1.0]
+    engine.free_model(model)
+
+
+@pytest.mark.parametrize("seed,m,n,dens", [(0, 7, 5, 0.5), (1, 40, 90, 0.1), (2, 300, 120, 0.03)])
+def test_arrays_roundtrip_and_csc(engine, pkg, seed, m, n, dens):
+    rng = np.random.default_rng(seed)
+    A = _rand_csr(rng, m, n, dens, empty_rows=(0, m - 1))
+    lp = dict(m=m, n=n, rowPtr=A.indptr, colIndex=A.indices, values=A.data, AL=rng.normal(size=m), AU=rng.normal(size=m) + 3,
+              l=np.zeros(n), u=np.full(n, np.inf), c=rng.normal(size=n))
+    model = engine.create_model(lp)
+    a = engine.model_arrays(model)
+    engine.free_model(model)
+    assert np.array_equal(a["rowPtr"], A.indptr) and np.array_equal(a["colIndex"], A.indices) and np.array_equal(a["values"], A.data)
+    for k in ("AL", "AU", "l", "u", "c"):
+        assert np.array_equal(a[k], lp[k])
+    # CSC input (is_csc=true) must produce the same CSR, entries ordered by column within each row
+    Acsc = A.tocsc(); Acsc.sort_indices()
+    lpc = dict(lp, rowPtr=Acsc.indptr, colIndex=Acsc.indices, values=Acsc.data)
+    model = engine.create_model(lpc, is_csc=True)
+    b = engine.model_arrays(model)
+    engine.free_model(model)
+    assert np.array_equal(b["rowPtr"], A.indptr) and np.array_equal(b["colIndex"], A.indices) and np.array_equal(b["values"], A.data)
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_arrays_bit_exact_vs_reference_build(engine, reference, seed):
+    rng = np.random.default_rng(seed)
+    m, n = 60, 45
+    A = _rand_csr(rng, m, n, 0.08, empty_rows=(5,))
+    Acsc = A.tocsc(); Acsc.sort_indices()
+    base = dict(m=m, n=n, AL=rng.normal(size=m), AU=rng.normal(size=m) + 3, l=np.zeros(n), u=np.full(n, np.inf), c=rng.normal(size=n))
+    for is_csc, M in ((False, A), (True, Acsc)):
+        lp = dict(base, rowPtr=M.indptr, colIndex=M.indices, values=M.data)
+        mine, ref = engine.create_model(lp, is_csc=is_csc), reference.create_model(lp, is_csc=is_csc)
+        a, b = engine.model_arrays(mine), reference.model_arrays(ref)
+        engine.free_model(mine); reference.free_model(ref)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (is_csc, k)
+
+
+def test_transpose_order_matches_reference_counting_sort(oracle):
+    """A^T entry order = stable counting sort by column (reference CSR_transpose_host, src/utils.cu:203-232):
+    within a transposed row, entries are ordered by original row index."""
+    rng = np.random.default_rng(7)
+    A = _rand_csr(rng, 50, 30, 0.2, empty_rows=(3,))
+    trp, tci, tv = oracle.transpose(50, 30, A.indptr, A.indices, A.data)
+    AT = A.T.tocsr(); AT.sort_indices()
+    assert np.array_equal(trp, AT.indptr) and np.array_equal(tci, AT.indices) and np.array_equal(tv, AT.data)
