@@ -19,6 +19,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 typedef struct {
     int max_iter;
@@ -473,4 +476,52 @@ double oracle_power(int m, int n, const int *rowPtr, const int *colIndex, const 
     double lam = power_method(&A, &AT, z0, max_iter, tol, iters);
     free(AT.rp); free(AT.ci); free(AT.v);
     return lam;
+}
+
+/* bench.py cpu_baseline leg: wall time of `iters` plain HPR iterations (x-phase + y-phase of
+ * HPR_cuda_kernels.cu:297-427) on the given, unscaled problem with sigma = lambda = 1 -- a bounded
+ * sample of the hot path on the host cores (OpenMP over rows).  Returns seconds. */
+double oracle_time_iterations(int m, int n, const int *rowPtr, const int *colIndex, const double *values,
+                              const double *AL, const double *AU, const double *l, const double *u, const double *c,
+                              int iters, int *threads_out) {
+    int nnz = rowPtr[m];
+    csr_t A = {m, n, nnz, (int *)rowPtr, (int *)colIndex, (double *)values};
+    csr_t AT = {n, m, nnz, (int *)malloc(sizeof(int) * (n + 1)), (int *)malloc(sizeof(int) * nnz),
+                (double *)malloc(sizeof(double) * nnz)};
+    oracle_transpose(m, n, nnz, rowPtr, colIndex, values, AT.rp, AT.ci, AT.v);
+    VEC(x, n); VEC(x0, n); VEC(x_hat, n); VEC(y, m); VEC(y0, m); VEC(w, n); VEC(ax, m);
+    int nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp single
+        nthreads = omp_get_num_threads();
+    }
+#endif
+    if (threads_out) *threads_out = nthreads;
+    const double sigma = 1.0, lamsig = 1.0, inv = 1.0;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int k = 0; k < iters; ++k) {
+        const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
+        spmv(&AT, y, w);
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < n; ++j) {
+            double xi = x[j], zt = fma(sigma, w[j] - c[j], xi);
+            double xb = fmin(u[j], fmax(l[j], zt)), xh = 2.0 * xb - xi;
+            x[j] = fma(f2, xh, f1 * x0[j]); x_hat[j] = xh;
+        }
+        spmv(&A, x_hat, ax);
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < m; ++i) {
+            double yi = y[i], v = fma(-lamsig, yi, ax[i]);
+            double d = fmax(AL[i] - v, fmin(AU[i] - v, 0.0));
+            double yb = inv * d, yh = 2.0 * yb - yi;
+            y[i] = fma(f2, yh, f1 * y0[i]);
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(AT.rp); free(AT.ci); free(AT.v);
+    free(x); free(x0); free(x_hat); free(y); free(y0); free(w); free(ax);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
