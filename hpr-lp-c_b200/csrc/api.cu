@@ -14,6 +14,7 @@
 #include "../../include/hprlp_b200.h"
 #include "../../include/version.h"
 #include "engine.h"
+#include <cuda_profiler_api.h>
 
 using hpr::Engine;
 using hpr::SolveHooks;
@@ -216,6 +217,9 @@ int hprlp_b200_scale_only(const LP_info_cpu *lp, const HPRLP_parameters *param_i
     }
     return 0;
 }
+
+void hprlp_b200_profiler_start(void) { cudaProfilerStart(); }
+void hprlp_b200_profiler_stop(void) { cudaProfilerStop(); }
 
 const char *hprlp_b200_version(void) { return "hprlp-b200 " HPRLP_ENGINE_STRING; }
 

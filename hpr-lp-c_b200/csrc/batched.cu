@@ -1,12 +1,370 @@
-// batched.cu -- solve_batched / free_batched_results (reference src/batched_solver.cu:939-1105).
+// batched.cu -- solve_batched / free_batched_results: B LPs sharing one sparse matrix A
+// (reference src/batched_solver.cu:939-1105 and its kernels :122-323).
+//
+// B200-native design (replaces cuSPARSE SpMM on column-major n x B matrices + flat elementwise kernels +
+// per-instance blocking cuBLAS reductions + a host sync every iteration):
+//   * device layout [group][row][32]: 32 instances ("a group") are contiguous, so every access to a
+//     batched vector is a 256-byte fully coalesced warp transaction; lane = instance.
+//   * fused SpMM + prox kernels: one warp per matrix row; the row's (col,val) pairs are loaded
+//     cooperatively once and broadcast by shuffle, each gather is one coalesced 256 B read of the
+//     dense row, the projection / dual update / Halpern averaging run in the epilogue -- A^T Y and
+//     A X_hat are never written to memory.  A is streamed once per group and stays L2 resident
+//     across groups (C4: 24 MB per copy vs 126 MB L2); groups are scheduled group-major so the
+//     gathered slab of one group (n x 32 doubles) is the L2 working set.
+//   * per-instance reductions (KKT residuals, objectives, restart gaps, movement norms) are
+//     accumulated per lane inside the same passes and reduced in a fixed order: one D2H of
+//     slots x B doubles per check instead of 5-6 blocking cuBLAS calls per instance.
+//   * per-instance sigma, Halpern counters and active/restart masks live on the device; the host
+//     only runs the restart/sigma/stopping logic at check points (no per-iteration sync).
+// Host logic (per-instance scaling with long-double norms, +-inf -> +-1e100, restart rules, sigma
+// update, `<=` stopping test, shared lambda_max bumped by max) restates the reference line by line.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
 
 #include "../../include/batched_solver.h"
 #include "engine.h"
+#include "kernels.cuh"
 
+namespace hpr {
 namespace {
+
+constexpr int kGS = 32;            // instances per group = lanes per warp
+constexpr int kBThreads = 256;     // 8 warps per CTA
+constexpr int kBWarps = kBThreads / 32;
+constexpr int kRowsPerCta = 32;    // 4 rows per warp
+constexpr double kInfReplacement = 1.0e100;   // reference src/batched_solver.cu:17
+
+struct BView {
+    int rows;          // rows of this matrix
+    int gcols;         // rows of the gathered dense operand (= columns of this matrix)
+    const int *rowPtr;
+    const int *col;
+    const double *val;
+};
+
+// ---------------------------------------------------------------------------------------------
+// skeleton: one warp per row, lane = instance of group blockIdx.y
+// ---------------------------------------------------------------------------------------------
+template <class Op>
+__global__ void __launch_bounds__(kBThreads) batched_rows_kernel(BView M, Op op) {
+    constexpr int NV = Op::NV;
+    __shared__ double red[kBWarps][kMaxSlots][kGS];
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    op.init(g, lane);
+    const int row0 = blockIdx.x * kRowsPerCta;
+    const int row1 = min(M.rows, row0 + kRowsPerCta);
+    const size_t gbase = (size_t)g * M.gcols;
+    for (int r = row0 + warp; r < row1; r += kBWarps) {
+        const int p0 = M.rowPtr[r], p1 = M.rowPtr[r + 1];
+        double acc[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+        for (int k0 = p0; k0 < p1; k0 += 32) {
+            const int kk = k0 + lane;
+            const int c = (kk < p1) ? __ldg(M.col + kk) : 0;
+            const double v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
+            const int cnt = min(32, p1 - k0);
+#pragma unroll 8
+            for (int t = 0; t < cnt; ++t) {
+                const int cc = __shfl_sync(0xffffffffu, c, t);
+                const double vv = __shfl_sync(0xffffffffu, v, t);
+                op.accum(vv, (gbase + cc) * kGS + lane, acc);
+            }
+        }
+        op.row(r, ((size_t)g * M.rows + r) * kGS + lane, acc);
+    }
+    op.finish(red, warp, lane);
+}
+
+template <int NS>
+__device__ __forceinline__ void batched_reduce_store(const double (&t)[NS], double (*red)[kMaxSlots][kGS], int warp, int lane,
+                                                     double *partials) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) red[warp][s][lane] = t[s];
+    __syncthreads();
+    if (warp == 0) {
+        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBWarps; ++w) v += red[w][s][lane];
+            partials[(blk * kMaxSlots + s) * kGS + lane] = v;
+        }
+    }
+}
+
+// out[s * Bpad + g*32 + lane] = sum over the nbx CTAs of group g, in block order
+__global__ void batched_final_reduce_kernel(const double *partials, int nbx, int ns, int Bpad, double *out) {
+    const int g = blockIdx.x, lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+    if (s >= ns) return;
+    double v = 0.0;
+    for (int b = 0; b < nbx; ++b) v += partials[(((size_t)g * nbx + b) * kMaxSlots + s) * kGS + lane];
+    out[(size_t)s * Bpad + g * kGS + lane] = v;
+}
+
+struct BOpBase {
+    static constexpr int NV = 1;
+    __device__ __forceinline__ void finish(double (*)[kMaxSlots][kGS], int, int) {}
+};
+
+// x-phase (reference update_x_z_{normal,check}_batched_kernel, src/batched_solver.cu:122-178)
+template <bool CHECK>
+struct BXOp : BOpBase {
+    const double *Y;
+    double *X, *X_hat;
+    const double *L, *U, *C, *lastX;
+    double *DX, *Z_bar, *X_bar;
+    const double *sigma;
+    const int *kx;
+    int *ky;
+    const unsigned char *active;
+    double sig, f1, f2;
+    bool on;
+    __device__ __forceinline__ void init(int g, int lane) {
+        const int inst = g * kGS + lane;
+        sig = sigma[inst];
+        on = active[inst] != 0;
+        const int k = kx[inst];
+        f1 = 1.0 / (k + 2.0);
+        f2 = 1.0 - f1;
+        if (blockIdx.x == 0 && threadIdx.x < 32) ky[inst] = k;
+    }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(Y + gi), acc[0]); }
+    __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
+        if (!on) return;
+        const double xi = X[t];
+        const double zt = fma(sig, acc[0] - C[t], xi);
+        const double xb = fmin(fmax(zt, L[t]), U[t]);
+        const double xh = 2.0 * xb - xi;
+        if (CHECK) {
+            DX[t] = xb - xh;
+            Z_bar[t] = (xb - zt) / sig;
+            X_bar[t] = xb;
+        }
+        X_hat[t] = xh;
+        X[t] = fma(f2, xh, f1 * lastX[t]);
+    }
+};
+
+// y-phase (reference update_y_{normal,check}_batched_kernel :180-236): y_bar = d / (lambda sigma) (a division
+// here, a reciprocal multiply in the single-instance path -- reference quirk #5)
+template <bool CHECK>
+struct BYOp : BOpBase {
+    const double *X_hat;
+    double *Y;
+    const double *AL, *AU, *lastY;
+    double *DY, *Y_bar, *Y_obj;
+    const double *sigma;
+    const int *ky;
+    int *kx;
+    const unsigned char *active;
+    double lambda_max;
+    double fact1, f1, f2;
+    bool on;
+    __device__ __forceinline__ void init(int g, int lane) {
+        const int inst = g * kGS + lane;
+        fact1 = lambda_max * sigma[inst];
+        on = active[inst] != 0;
+        const int k = ky[inst];
+        f1 = 1.0 / (k + 2.0);
+        f2 = 1.0 - f1;
+        if (blockIdx.x == 0 && threadIdx.x < 32 && on) kx[inst] = k + 1;
+    }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(X_hat + gi), acc[0]); }
+    __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
+        if (!on) return;
+        const double yi = Y[t];
+        const double v = fma(-fact1, yi, acc[0]);
+        const double d = fmax(AL[t] - v, fmin(AU[t] - v, 0.0));
+        const double yb = d / fact1;
+        const double yh = 2.0 * yb - yi;
+        if (CHECK) {
+            DY[t] = yb - yh;
+            Y_bar[t] = yb;
+            Y_obj[t] = v + d;
+        }
+        Y[t] = fma(f2, yh, f1 * lastY[t]);
+    }
+};
+
+// dual residual + objective terms (reference compute_batched_Rd_kernel :238-249 + cublasDdot/Dnrm2 :604-607,
+// lu violation :265-278,615-617): slots 0 |RD|^2, 1 <C,X_bar>, 2 <X_bar,Z_bar>, 3 |lu/col_norm|^2 (iter 0)
+template <bool ITER0>
+struct BResDualOp : BOpBase {
+    const double *Y_bar, *C, *Z_bar, *X_bar, *L, *U, *col_norm;
+    double *partials;
+    double t[4];
+    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = t[2] = t[3] = 0.0; }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(Y_bar + gi), acc[0]); }
+    __device__ __forceinline__ void row(int j, size_t i, const double (&acc)[1]) {
+        const double cj = C[i], zb = Z_bar[i], xb = X_bar[i], cn = col_norm[j];
+        const double rd = (cj - acc[0] - zb) * cn;
+        t[0] += rd * rd;
+        t[1] += cj * xb;
+        t[2] += xb * zb;
+        if (ITER0) {
+            const double lo = L[i], hi = U[i];
+            const double viol = xb < lo ? lo - xb : (xb > hi ? xb - hi : 0.0);
+            const double q = viol / cn;
+            t[3] += q * q;
+        }
+    }
+    __device__ __forceinline__ void finish(double (*red)[kMaxSlots][kGS], int warp, int lane) {
+        batched_reduce_store<4>(t, red, warp, lane, partials);
+    }
+};
+
+// primal residual (reference compute_batched_Rp_kernel :251-263 + :605,608): slots 0 |RP|^2, 1 <Y_obj,Y_bar>
+struct BResPrimalOp : BOpBase {
+    const double *X_bar, *AL, *AU, *row_norm, *Y_obj, *Y_bar;
+    double *partials;
+    double t[2];
+    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(X_bar + gi), acc[0]); }
+    __device__ __forceinline__ void row(int r, size_t i, const double (&acc)[1]) {
+        const double ax = acc[0];
+        const double rp = row_norm[r] * fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax);
+        t[0] += rp * rp;
+        t[1] += Y_obj[i] * Y_bar[i];
+    }
+    __device__ __forceinline__ void finish(double (*red)[kMaxSlots][kGS], int warp, int lane) {
+        batched_reduce_store<2>(t, red, warp, lane, partials);
+    }
+};
+
+// M-norm terms (reference compute_weighted_norm :625-650): slots 0 <A DX, DY>, 1 |DY|^2
+struct BWeightedOp : BOpBase {
+    const double *DX, *DY;
+    double *partials;
+    double t[2];
+    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(DX + gi), acc[0]); }
+    __device__ __forceinline__ void row(int, size_t i, const double (&acc)[1]) {
+        const double dy = DY[i];
+        t[0] += acc[0] * dy;
+        t[1] += dy * dy;
+    }
+    __device__ __forceinline__ void finish(double (*red)[kMaxSlots][kGS], int warp, int lane) {
+        batched_reduce_store<2>(t, red, warp, lane, partials);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// dense [group][row][32] vector kernels: grid (chunks, groups), warp per row
+// ---------------------------------------------------------------------------------------------
+// per-instance |V|^2
+__global__ void __launch_bounds__(kBThreads) batched_sumsq_kernel(const double *V, int rows, double *partials) {
+    __shared__ double red[kBWarps][kMaxSlots][kGS];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double t[1] = {0.0};
+    for (int r = blockIdx.x * kBWarps + warp; r < rows; r += gridDim.x * kBWarps) {
+        const double v = V[((size_t)g * rows + r) * kGS + lane];
+        t[0] += v * v;
+    }
+    batched_reduce_store<1>(t, red, warp, lane, partials);
+}
+
+// movement norms (reference batched_restart_movement_kernel :280-294 + nrm2 :661-664) fused with the masked
+// restart copy (do_batched_restart_kernel :296-323): slots 0 |X_bar-lastX|^2, 1 |Y_bar-lastY|^2
+__global__ void __launch_bounds__(kBThreads) batched_restart_kernel(const double *X_bar, double *lastX, double *X, int n, const double *Y_bar,
+                                                                   double *lastY, double *Y, int m, const unsigned char *flags,
+                                                                   int *kx, double *partials) {
+    __shared__ double red[kBWarps][kMaxSlots][kGS];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool flag = flags[g * kGS + lane] != 0;
+    double t[2] = {0.0, 0.0};
+    for (int r = blockIdx.x * kBWarps + warp; r < n; r += gridDim.x * kBWarps) {
+        const size_t i = ((size_t)g * n + r) * kGS + lane;
+        const double xb = X_bar[i], d = xb - lastX[i];
+        t[0] += d * d;
+        if (flag) { lastX[i] = xb; X[i] = xb; }
+    }
+    for (int r = blockIdx.x * kBWarps + warp; r < m; r += gridDim.x * kBWarps) {
+        const size_t i = ((size_t)g * m + r) * kGS + lane;
+        const double yb = Y_bar[i], d = yb - lastY[i];
+        t[1] += d * d;
+        if (flag) { lastY[i] = yb; Y[i] = yb; }
+    }
+    if (blockIdx.x == 0 && warp == 0 && flag) kx[g * kGS + lane] = 0;   // Halpern counter reset for restarted instances
+    batched_reduce_store<2>(t, red, warp, lane, partials);
+}
+
+// column-major host layout (instance k, row i at k*rows + i) <-> device layout [g][i][32]
+__global__ void to_group_layout_kernel(const double *src, double *dst, int rows, int B, double pad) {
+    __shared__ double tile[32][33];
+    const int g = blockIdx.y, r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int inst = g * kGS + k, r = r0 + tx;
+        tile[k][tx] = (inst < B && r < rows) ? src[(size_t)inst * rows + r] : pad;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int r = r0 + k;
+        if (r < rows) dst[((size_t)g * rows + r) * kGS + tx] = tile[tx][k];
+    }
+}
+// device layout -> column-major with unscaling: out = (v (/|*) norm[row]) * scale[instance]
+// (reference collect_results :915-924)
+template <bool DIVIDE>
+__global__ void from_group_layout_kernel(const double *src, double *dst, int rows, int B, const double *norm, const double *scale) {
+    __shared__ double tile[32][33];
+    const int g = blockIdx.y, r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int r = r0 + k;
+        if (r < rows) {
+            const double v = src[((size_t)g * rows + r) * kGS + tx];
+            const double nr = norm[r];
+            tile[k][tx] = (DIVIDE ? v / nr : v * nr) * scale[g * kGS + tx];
+        }
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int inst = g * kGS + k, r = r0 + tx;
+        if (inst < B && r < rows) dst[(size_t)inst * rows + r] = tile[tx][k];
+    }
+}
+
+template <typename T>
+T *balloc(size_t count) {
+    T *p = nullptr;
+    HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    return p;
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int step_of(int iter) { return std::max(10, static_cast<int>(pow(10, floor(log10((double)iter))) / 10)); }
+
+// reference bound_norm_host / column_norm_host (:332-354): long-double accumulation on the host
+double bound_norm_host(const double *AL, const double *AU, int m) {
+    long double sum = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double lo = AL[i], hi = AU[i];
+        const double a = std::isinf(lo) && lo < 0 ? 0.0 : std::abs(lo);
+        const double b = std::isinf(hi) && hi > 0 ? 0.0 : std::abs(hi);
+        const double v = std::max(a, b);
+        sum += static_cast<long double>(v) * v;
+    }
+    return std::sqrt(static_cast<double>(sum));
+}
+double column_norm_host(const double *X, int n) {
+    long double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += static_cast<long double>(X[i]) * X[i];
+    return std::sqrt(static_cast<double>(sum));
+}
+
 HPRLP_batched_results make_batched_error(const char *status, int m, int n, int B) {   // reference :356-368
     HPRLP_batched_results r;
     r.m = m; r.n = n; r.batch_size = B;
@@ -16,17 +374,408 @@ HPRLP_batched_results make_batched_error(const char *status, int m, int n, int B
     }
     return r;
 }
-}  // namespace
 
-extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C,
-                                                const HPRLP_FLOAT *AL, const HPRLP_FLOAT *AU, const HPRLP_FLOAT *l,
-                                                const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
+struct RestartHost {   // reference BatchedRestartHost :103-120
+    std::vector<int> restart_flag, inner, times;
+    std::vector<unsigned char> first_restart;
+    std::vector<double> last_gap, current_gap, save_gap, best_gap, best_sigma, sigma;
+};
+
+struct ResidualHost {   // reference BatchedResidualHost :94-101
+    std::vector<double> primal_obj, dual_obj, err_Rp, err_Rd, rel_gap, kkt_error;
+};
+
+class BatchedSolver {
+   public:
+    Engine eng;   // shared matrix: upload, scaling (bc off), power iteration
+    int m = 0, n = 0, B = 0, G = 0, Bpad = 0;
+    double *X = nullptr, *X_hat = nullptr, *X_bar = nullptr, *DX = nullptr, *Z_bar = nullptr, *lastX = nullptr;
+    double *C = nullptr, *L = nullptr, *U = nullptr;
+    double *Y = nullptr, *Y_bar = nullptr, *DY = nullptr, *Y_obj = nullptr, *lastY = nullptr, *AL = nullptr, *AU = nullptr;
+    double *d_sigma = nullptr, *d_scale_b = nullptr, *d_scale_c = nullptr;
+    int *d_k = nullptr;   // [kx (Bpad), ky (Bpad)]
+    unsigned char *d_active = nullptr, *d_flags = nullptr;
+    double *d_partials = nullptr, *d_scal = nullptr, *h_scal = nullptr;
+    double *d_stage = nullptr;   // column-major staging buffer, max(n,m) * B
+    double lambda_max = 1.0;
+    cudaStream_t stream = nullptr;
+    int nbx_A = 0, nbx_AT = 0, nbx_vec = 0;
+    long long launches = 0;
+    std::vector<double> b_scale, c_scale, norm_b, norm_c, norm_b_org, norm_c_org, obj_constants;
+    std::vector<double> row_norm_h, col_norm_h;
+
+    ~BatchedSolver() {
+        for (void *p : {(void *)X, (void *)X_hat, (void *)X_bar, (void *)DX, (void *)Z_bar, (void *)lastX, (void *)C, (void *)L, (void *)U,
+                        (void *)Y, (void *)Y_bar, (void *)DY, (void *)Y_obj, (void *)lastY, (void *)AL, (void *)AU, (void *)d_sigma,
+                        (void *)d_scale_b, (void *)d_scale_c, (void *)d_k, (void *)d_active, (void *)d_flags, (void *)d_partials,
+                        (void *)d_scal, (void *)d_stage})
+            if (p) cudaFree(p);
+        if (h_scal) cudaFreeHost(h_scal);
+    }
+
+    BView viewA() const { return BView{m, n, eng.A.rowPtr, eng.A.col, eng.A.val}; }
+    BView viewAT() const { return BView{n, m, eng.AT.rowPtr, eng.AT.col, eng.AT.val}; }
+    dim3 gridA() const { return dim3(nbx_A, G); }
+    dim3 gridAT() const { return dim3(nbx_AT, G); }
+
+    void upload_dense(const double *host, double *dst, int rows, double pad) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * (size_t)rows * B, cudaMemcpyHostToDevice, stream));
+        to_group_layout_kernel<<<dim3((rows + 31) / 32, G), 256, 0, stream>>>(d_stage, dst, rows, B, pad);
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // staging buffer is reused
+        launches++;
+    }
+
+    void fetch(int slots) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * (size_t)slots * Bpad, cudaMemcpyDeviceToHost, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    double hs(int slot, int k) const { return h_scal[(size_t)slot * Bpad + k]; }
+
+    void iteration(bool check) {
+        const int *kx = d_k; int *kxw = d_k; int *ky = d_k + Bpad;
+        if (check) {
+            BXOp<true> ox{}; ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
+            ox.DX = DX; ox.Z_bar = Z_bar; ox.X_bar = X_bar; ox.sigma = d_sigma; ox.kx = kx; ox.ky = ky; ox.active = d_active;
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), ox);
+            BYOp<true> oy{}; oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY; oy.DY = DY; oy.Y_bar = Y_bar;
+            oy.Y_obj = Y_obj; oy.sigma = d_sigma; oy.ky = ky; oy.kx = kxw; oy.active = d_active; oy.lambda_max = lambda_max;
+            batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), oy);
+        } else {
+            BXOp<false> ox{}; ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
+            ox.sigma = d_sigma; ox.kx = kx; ox.ky = ky; ox.active = d_active;
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), ox);
+            BYOp<false> oy{}; oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY;
+            oy.sigma = d_sigma; oy.ky = ky; oy.kx = kxw; oy.active = d_active; oy.lambda_max = lambda_max;
+            batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), oy);
+        }
+        launches += 2;
+    }
+
+    // reference compute_weighted_norm :625-650 (lambda_max shared by the batch, only ever increased)
+    std::vector<double> weighted_norm(const std::vector<double> &sigma) {
+        BWeightedOp o{}; o.DX = DX; o.DY = DY; o.partials = d_partials;
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), o);
+        batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal);
+        batched_sumsq_kernel<<<dim3(nbx_vec, G), kBThreads, 0, stream>>>(DX, n, d_partials);
+        batched_final_reduce_kernel<<<G, 32, 0, stream>>>(d_partials, nbx_vec, 1, Bpad, d_scal + 2 * (size_t)Bpad);
+        launches += 4;
+        fetch(3);
+        std::vector<double> w(B, 0.0);
+        for (int k = 0; k < B; ++k) {
+            const double dot_prod = 2.0 * hs(0, k), dy_sq = hs(1, k), dx_sq = hs(2, k);
+            double value = sigma[k] * (lambda_max * dy_sq) + dx_sq / sigma[k] + dot_prod;
+            if (value < 0.0 && dy_sq > 0.0) {
+                const double cand = -(dot_prod + dx_sq / sigma[k]) / (sigma[k] * dy_sq) * 1.05;
+                lambda_max = std::max(lambda_max, cand);
+                value = sigma[k] * (lambda_max * dy_sq) + dx_sq / sigma[k] + dot_prod;
+            }
+            w[k] = std::sqrt(std::max(value, 0.0));
+        }
+        return w;
+    }
+
+    // reference compute_residuals :578-623
+    void residuals(int iter, ResidualHost *res) {
+        if (iter == 0) {
+            BResDualOp<true> o{}; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
+            o.col_norm = eng.col_norm; o.partials = d_partials;
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o);
+        } else {
+            BResDualOp<false> o{}; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
+            o.col_norm = eng.col_norm; o.partials = d_partials;
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o);
+        }
+        batched_final_reduce_kernel<<<G, 32 * 4, 0, stream>>>(d_partials, nbx_AT, 4, Bpad, d_scal);
+        BResPrimalOp p{}; p.X_bar = X_bar; p.AL = AL; p.AU = AU; p.row_norm = eng.row_norm; p.Y_obj = Y_obj; p.Y_bar = Y_bar;
+        p.partials = d_partials;
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), p);
+        batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal + 4 * (size_t)Bpad);
+        launches += 4;
+        fetch(6);
+        for (int k = 0; k < B; ++k) {
+            const double obj_scale = b_scale[k] * c_scale[k];
+            res->primal_obj[k] = obj_scale * hs(1, k) + obj_constants[k];
+            res->dual_obj[k] = obj_scale * (hs(5, k) + hs(2, k)) + obj_constants[k];
+            res->err_Rd[k] = c_scale[k] * std::sqrt(hs(0, k)) / norm_c_org[k];
+            res->err_Rp[k] = b_scale[k] * std::sqrt(hs(4, k)) / norm_b_org[k];
+            if (iter == 0) res->err_Rp[k] = std::max(res->err_Rp[k], b_scale[k] * std::sqrt(hs(3, k)));
+            res->rel_gap[k] = std::abs(res->primal_obj[k] - res->dual_obj[k]) /
+                              (1.0 + std::abs(res->primal_obj[k]) + std::abs(res->dual_obj[k]));
+            res->kkt_error[k] = std::max(res->err_Rp[k], std::max(res->err_Rd[k], res->rel_gap[k]));
+        }
+    }
+};
+
+// reference check_restart :667-700
+void check_restart(RestartHost *r, int iter, int check_iter, const std::vector<unsigned char> &active) {
+    for (int k = 0; k < (int)active.size(); ++k) {
+        if (!active[k]) continue;
+        if (r->first_restart[k]) {
+            if (iter == check_iter) {
+                r->first_restart[k] = 0;
+                r->restart_flag[k] = 1;
+                r->best_gap[k] = r->current_gap[k];
+                r->best_sigma[k] = r->sigma[k];
+            }
+        } else if (iter % check_iter == 0) {
+            if (r->current_gap[k] < 0.0) r->current_gap[k] = 1.0e-6;
+            if (r->current_gap[k] <= 0.2 * r->last_gap[k]) r->restart_flag[k] = 1;
+            if (r->current_gap[k] <= 0.6 * r->last_gap[k] && r->current_gap[k] > r->save_gap[k]) r->restart_flag[k] = 2;
+            if (r->inner[k] >= 0.2 * iter) r->restart_flag[k] = 3;
+            if (r->best_gap[k] > r->current_gap[k]) { r->best_gap[k] = r->current_gap[k]; r->best_sigma[k] = r->sigma[k]; }
+            r->save_gap[k] = r->current_gap[k];
+        }
+    }
+}
+
+}  // namespace
+}  // namespace hpr
+
+using namespace hpr;
+
+extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
+                                                const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in, const HPRLP_FLOAT *l_in,
+                                                const HPRLP_FLOAT *u_in, const HPRLP_FLOAT *obj_constants,
                                                 const HPRLP_parameters *param) {
-    (void)obj_constants; (void)param;
-    if (!model || !model->A || batch_size <= 0 || !C || !AL || !AU || !l || !u) {
+    if (!model || !model->A || batch_size <= 0 || !C_in || !AL_in || !AU_in || !l_in || !u_in) {
         return make_batched_error("ERROR", model ? model->m : 0, model ? model->n : 0, std::max(batch_size, 0));
     }
-    return make_batched_error("ERROR", model->m, model->n, batch_size);
+    HPRLP_parameters def;
+    HPRLP_parameters actual = param ? *param : def;
+    actual.use_presolve = false;
+    const double setup_start = now_s();
+    const int m = model->m, n = model->n, B = batch_size;
+
+    BatchedSolver S;
+    S.m = m; S.n = n; S.B = B; S.G = (B + kGS - 1) / kGS; S.Bpad = S.G * kGS;
+    // shared matrix on the device with dummy vectors; matrix-only scaling (bc off) -- reference :959-989
+    {
+        std::vector<double> zero_m(m, 0.0), zero_n(n, 0.0);
+        LP_info_cpu mat{};
+        mat.m = m; mat.n = n; mat.A = model->A;
+        mat.AL = zero_m.data(); mat.AU = zero_m.data(); mat.c = zero_n.data(); mat.l = zero_n.data(); mat.u = zero_n.data();
+        mat.obj_constant = 0.0;
+        S.eng.upload(&mat, actual.device_number);
+        HPRLP_parameters mp = actual;
+        mp.use_bc_scaling = false;
+        S.eng.scale(&mp);
+    }
+    S.stream = S.eng.stream;
+    S.row_norm_h.resize(m); S.col_norm_h.resize(n);
+    HPR_CUDA_CHECK(cudaMemcpy(S.row_norm_h.data(), S.eng.row_norm, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    HPR_CUDA_CHECK(cudaMemcpy(S.col_norm_h.data(), S.eng.col_norm, sizeof(double) * n, cudaMemcpyDeviceToHost));
+
+    // per-instance scaling on the host -- reference build_batched_lp_device :792-885
+    std::vector<double> hC(C_in, C_in + (size_t)n * B), hAL(AL_in, AL_in + (size_t)m * B), hAU(AU_in, AU_in + (size_t)m * B);
+    std::vector<double> hL(l_in, l_in + (size_t)n * B), hU(u_in, u_in + (size_t)n * B);
+    S.b_scale.assign(B, 1.0); S.c_scale.assign(B, 1.0); S.norm_b.assign(B, 0.0); S.norm_c.assign(B, 0.0);
+    S.norm_b_org.assign(B, 1.0); S.norm_c_org.assign(B, 1.0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < B; ++k) {
+        double *al = hAL.data() + (size_t)k * m, *au = hAU.data() + (size_t)k * m;
+        double *cc = hC.data() + (size_t)k * n, *ll = hL.data() + (size_t)k * n, *uu = hU.data() + (size_t)k * n;
+        S.norm_b_org[k] = 1.0 + bound_norm_host(al, au, m);
+        S.norm_c_org[k] = 1.0 + column_norm_host(cc, n);
+        for (int i = 0; i < m; ++i) { const double rn = S.row_norm_h[i]; al[i] /= rn; au[i] /= rn; }
+        for (int i = 0; i < n; ++i) { const double cn = S.col_norm_h[i]; cc[i] /= cn; ll[i] *= cn; uu[i] *= cn; }
+        if (actual.use_bc_scaling) {
+            S.b_scale[k] = 1.0 + bound_norm_host(al, au, m);
+            S.c_scale[k] = 1.0 + column_norm_host(cc, n);
+            for (int i = 0; i < m; ++i) { al[i] /= S.b_scale[k]; au[i] /= S.b_scale[k]; }
+            for (int i = 0; i < n; ++i) { cc[i] /= S.c_scale[k]; ll[i] /= S.b_scale[k]; uu[i] /= S.b_scale[k]; }
+        }
+        S.norm_b[k] = bound_norm_host(al, au, m);
+        S.norm_c[k] = column_norm_host(cc, n);
+        for (int i = 0; i < m; ++i) {
+            if (std::isinf(al[i]) && al[i] < 0) al[i] = -kInfReplacement;
+            if (std::isinf(au[i]) && au[i] > 0) au[i] = kInfReplacement;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (std::isinf(ll[i]) && ll[i] < 0) ll[i] = -kInfReplacement;
+            if (std::isinf(uu[i]) && uu[i] > 0) uu[i] = kInfReplacement;
+        }
+    }
+    S.obj_constants.assign(B, model->obj_constant);
+    if (obj_constants) S.obj_constants.assign(obj_constants, obj_constants + B);
+
+    // device state
+    const size_t nG = (size_t)n * S.Bpad, mG = (size_t)m * S.Bpad;
+    S.X = balloc<double>(nG); S.X_hat = balloc<double>(nG); S.X_bar = balloc<double>(nG); S.DX = balloc<double>(nG);
+    S.Z_bar = balloc<double>(nG); S.lastX = balloc<double>(nG); S.C = balloc<double>(nG); S.L = balloc<double>(nG); S.U = balloc<double>(nG);
+    S.Y = balloc<double>(mG); S.Y_bar = balloc<double>(mG); S.DY = balloc<double>(mG); S.Y_obj = balloc<double>(mG);
+    S.lastY = balloc<double>(mG); S.AL = balloc<double>(mG); S.AU = balloc<double>(mG);
+    S.d_sigma = balloc<double>(S.Bpad); S.d_scale_b = balloc<double>(S.Bpad); S.d_scale_c = balloc<double>(S.Bpad);
+    S.d_k = balloc<int>(2 * (size_t)S.Bpad);
+    S.d_active = balloc<unsigned char>(S.Bpad); S.d_flags = balloc<unsigned char>(S.Bpad);
+    S.nbx_A = (m + kRowsPerCta - 1) / kRowsPerCta;
+    S.nbx_AT = (n + kRowsPerCta - 1) / kRowsPerCta;
+    S.nbx_vec = std::max(1, std::min((std::max(m, n) + kBWarps - 1) / kBWarps, 148 * 2));
+    const size_t nblk = (size_t)std::max(std::max(S.nbx_A, S.nbx_AT), S.nbx_vec) * S.G;
+    S.d_partials = balloc<double>(nblk * kMaxSlots * kGS);
+    S.d_scal = balloc<double>((size_t)kMaxSlots * S.Bpad);
+    HPR_CUDA_CHECK(cudaMallocHost(&S.h_scal, sizeof(double) * kMaxSlots * S.Bpad));
+    S.d_stage = balloc<double>((size_t)std::max(m, n) * B);
+    S.upload_dense(hC.data(), S.C, n, 0.0);
+    S.upload_dense(hL.data(), S.L, n, 0.0);
+    S.upload_dense(hU.data(), S.U, n, 0.0);
+    S.upload_dense(hAL.data(), S.AL, m, 0.0);
+    S.upload_dense(hAU.data(), S.AU, m, 0.0);
+
+    // power iteration on the shared, scaled matrix -- reference :994-1001
+    const double power_start = now_s();
+    S.lambda_max = S.eng.power_iteration(5000, 1.0e-4, nullptr, nullptr) * 1.01;
+    const double power_time = now_s() - power_start;
+
+    RestartHost R;
+    R.restart_flag.assign(B, 0); R.first_restart.assign(B, 1); R.inner.assign(B, 0); R.times.assign(B, 0);
+    const double inf = std::numeric_limits<double>::infinity();
+    R.last_gap.assign(B, inf); R.current_gap.assign(B, inf); R.save_gap.assign(B, inf); R.best_gap.assign(B, inf);
+    R.sigma.assign(B, 1.0);
+    for (int k = 0; k < B; ++k)
+        if (S.norm_b[k] > 1.0e-8 && S.norm_c[k] > 1.0e-8) R.sigma[k] = S.norm_b[k] / S.norm_c[k];
+    R.best_sigma = R.sigma;
+    std::vector<double> sig_pad(S.Bpad, 1.0), bs_pad(S.Bpad, 1.0), cs_pad(S.Bpad, 1.0);
+    std::vector<unsigned char> active(B, 1), act_pad(S.Bpad, 0), flag_pad(S.Bpad, 0);
+    for (int k = 0; k < B; ++k) { sig_pad[k] = R.sigma[k]; bs_pad[k] = S.b_scale[k]; cs_pad[k] = S.c_scale[k]; act_pad[k] = 1; }
+    HPR_CUDA_CHECK(cudaMemcpy(S.d_sigma, sig_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice));
+    HPR_CUDA_CHECK(cudaMemcpy(S.d_scale_b, bs_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice));
+    HPR_CUDA_CHECK(cudaMemcpy(S.d_scale_c, cs_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice));
+    HPR_CUDA_CHECK(cudaMemcpy(S.d_active, act_pad.data(), S.Bpad, cudaMemcpyHostToDevice));
+    const double setup_time = now_s() - setup_start;
+
+    const double solve_start = now_s();
+    ResidualHost res;
+    res.primal_obj.assign(B, 0.0); res.dual_obj.assign(B, 0.0); res.err_Rp.assign(B, 0.0); res.err_Rd.assign(B, 0.0);
+    res.rel_gap.assign(B, 0.0); res.kkt_error.assign(B, inf);
+    std::vector<std::string> status(B, "CONTINUE");
+    std::vector<int> final_iter(B, actual.max_iter);
+    const int check_iter = std::max(actual.check_iter, 1);
+
+    auto upload_active = [&]() {
+        for (int k = 0; k < B; ++k) act_pad[k] = active[k];
+        HPR_CUDA_CHECK(cudaMemcpyAsync(S.d_active, act_pad.data(), S.Bpad, cudaMemcpyHostToDevice, S.stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
+    };
+
+    int iter = 0;
+    const char *final_status = nullptr;
+    for (;;) {   // visited indices: multiples of check_iter and max_iter (reference loop :1017-1084)
+        const bool periodic = (iter % check_iter) == 0;
+        const double elapsed = now_s() - solve_start;
+        if (periodic) {
+            if (iter > 0) R.current_gap = S.weighted_norm(R.sigma);
+            S.residuals(iter, &res);
+            for (int k = 0; k < B; ++k)
+                if (active[k] && res.kkt_error[k] <= actual.stop_tol) {   // `<=`: reference quirk #4
+                    status[k] = "OPTIMAL";
+                    final_iter[k] = iter;
+                    active[k] = 0;
+                }
+            upload_active();
+        }
+        bool all_done = true;
+        for (const std::string &s : status) all_done = all_done && (s != "CONTINUE");
+        if (all_done) break;
+        if (iter >= actual.max_iter || elapsed >= actual.time_limit) {
+            final_status = elapsed >= actual.time_limit ? "TIME_LIMIT" : "ITER_LIMIT";
+            for (int k = 0; k < B; ++k)
+                if (status[k] == "CONTINUE") { status[k] = final_status; final_iter[k] = iter; active[k] = 0; }
+            break;
+        }
+        std::fill(R.restart_flag.begin(), R.restart_flag.end(), 0);
+        if (periodic) check_restart(&R, iter, check_iter, active);
+
+        bool any = false;
+        for (int f : R.restart_flag) any = any || (f >= 1 && f <= 3);
+        if (any) {
+            // update_sigma + do_restart (reference :702-762): movement norms for all, masked copies for the restarted
+            for (int k = 0; k < B; ++k) flag_pad[k] = R.restart_flag[k] > 0 ? 1 : 0;
+            HPR_CUDA_CHECK(cudaMemcpyAsync(S.d_flags, flag_pad.data(), S.Bpad, cudaMemcpyHostToDevice, S.stream));
+            batched_restart_kernel<<<dim3(S.nbx_vec, S.G), kBThreads, 0, S.stream>>>(S.X_bar, S.lastX, S.X, n, S.Y_bar, S.lastY, S.Y, m,
+                                                                                    S.d_flags, S.d_k, S.d_partials);
+            batched_final_reduce_kernel<<<S.G, 32 * 2, 0, S.stream>>>(S.d_partials, S.nbx_vec, 2, S.Bpad, S.d_scal);
+            S.launches += 2;
+            S.fetch(2);
+            const double sqrt_lambda = std::sqrt(S.lambda_max);
+            for (int k = 0; k < B; ++k) {
+                if (!active[k] || R.restart_flag[k] < 1) continue;
+                const double pm = std::sqrt(S.hs(0, k)), dm = std::sqrt(S.hs(1, k));
+                if (pm > 1.0e-16 && dm > 1.0e-16 && pm < 1.0e12 && dm < 1.0e12) {
+                    const double ratio = (pm / dm) / sqrt_lambda;
+                    const double fact = std::exp(-0.05 * (R.current_gap[k] / R.best_gap[k]));
+                    const double temp1 = std::max(std::min(res.err_Rd[k], res.err_Rp[k]), std::min(res.rel_gap[k], R.current_gap[k]));
+                    const double sigma_cand = std::exp(fact * std::log(ratio) + (1.0 - fact) * std::log(R.best_sigma[k]));
+                    const double ratio_infeas = res.err_Rd[k] / res.err_Rp[k];
+                    double kappa = 1.0;
+                    if (temp1 > 9.0e-10) kappa = 1.0;
+                    else if (temp1 > 5.0e-10) kappa = std::max(std::min(std::sqrt(ratio_infeas), 100.0), 1.0e-2);
+                    else kappa = std::max(std::min(ratio_infeas, 100.0), 1.0e-2);
+                    R.sigma[k] = kappa * sigma_cand;
+                } else {
+                    R.sigma[k] = 1.0;
+                }
+                R.times[k] += 1;
+                R.inner[k] = 0;
+                R.save_gap[k] = inf;
+            }
+            for (int k = 0; k < B; ++k) sig_pad[k] = R.sigma[k];
+            HPR_CUDA_CHECK(cudaMemcpyAsync(S.d_sigma, sig_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice, S.stream));
+            HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
+        }
+
+        // run to the next visited index; check iterations where the reference's to_check holds (:1067-1068)
+        long long next = ((long long)iter / check_iter + 1) * check_iter;
+        if ((long long)actual.max_iter > iter) next = std::min(next, (long long)actual.max_iter);
+        const int stop = (int)std::min<long long>(next, INT32_MAX);
+        for (int it = iter; it < stop; ++it) {
+            const bool restarted = any && it == iter;
+            const bool to_check = ((it + 1) % check_iter) == 0 || restarted || ((it + 1) % step_of(it + 1) == 0);
+            S.iteration(to_check);
+            if (restarted) {
+                std::vector<double> lg = S.weighted_norm(R.sigma);
+                for (int k = 0; k < B; ++k)
+                    if (R.restart_flag[k] > 0) R.last_gap[k] = lg[k];
+            }
+        }
+        for (int k = 0; k < B; ++k)
+            if (active[k]) R.inner[k] += stop - iter;
+        iter = stop;
+    }
+    HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
+    const double solve_time = now_s() - solve_start;
+
+    // collect_results (reference :887-935): unscale on the device, one D2H per output array
+    HPRLP_batched_results out;
+    out.m = m; out.n = n; out.batch_size = B;
+    out.x = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    out.y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)m * B));
+    out.z = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    out.primal_obj = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.residuals = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.gap = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.iter = static_cast<int *>(std::malloc(sizeof(int) * B));
+    out.status = static_cast<char *>(std::calloc(static_cast<size_t>(B) * 64, sizeof(char)));
+    auto download = [&](const double *src, double *dst, int rows, bool divide, const double *norm, const double *scale) {
+        if (divide) from_group_layout_kernel<true><<<dim3((rows + 31) / 32, S.G), 256, 0, S.stream>>>(src, S.d_stage, rows, B, norm, scale);
+        else from_group_layout_kernel<false><<<dim3((rows + 31) / 32, S.G), 256, 0, S.stream>>>(src, S.d_stage, rows, B, norm, scale);
+        HPR_CUDA_CHECK(cudaMemcpyAsync(dst, S.d_stage, sizeof(double) * (size_t)rows * B, cudaMemcpyDeviceToHost, S.stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
+    };
+    download(S.X_bar, out.x, n, true, S.eng.col_norm, S.d_scale_b);
+    download(S.Z_bar, out.z, n, false, S.eng.col_norm, S.d_scale_c);
+    download(S.Y_bar, out.y, m, true, S.eng.row_norm, S.d_scale_c);
+    for (int k = 0; k < B; ++k) {
+        out.primal_obj[k] = res.primal_obj[k];
+        out.residuals[k] = res.kkt_error[k];
+        out.gap[k] = res.rel_gap[k];
+        out.iter[k] = final_iter[k];
+        std::strncpy(out.status + 64 * k, status[k].c_str(), 63);
+    }
+    out.setup_time = setup_time;
+    out.solve_time = solve_time;
+    out.power_time = power_time;
+    out.time = setup_time + solve_time;
+    return out;
 }
 
 extern "C" void free_batched_results(HPRLP_batched_results *results) {   // reference :1094-1105
