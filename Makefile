@@ -11,7 +11,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC \
            -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xcompiler -fopenmp -Iinclude
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CUDA_PATH)/include
-LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp
+LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread
 RPATH := -Xlinker -rpath -Xlinker $(CUDA_PATH)/lib64
 
 CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu

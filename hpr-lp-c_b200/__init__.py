@@ -91,7 +91,7 @@ REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve
 EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
                     "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
                     "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
-                    "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
+                    "hprlp_b200_solve_batched_multi", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
 
 
 def _dp(a):
@@ -159,6 +159,8 @@ class HprLib:
             L.hprlp_b200_scale_only.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)] + [c_double_p, c_int_p, c_int_p] + \
                 [c_double_p] * 9
             L.hprlp_b200_version.restype = C.c_char_p
+            L.hprlp_b200_solve_batched_multi.restype = BatchedResults
+            L.hprlp_b200_solve_batched_multi.argtypes = L.solve_batched.argtypes + [C.c_int]
 
     # -- model layer -----------------------------------------------------------------------------
     def create_model(self, lp, is_csc=False):
@@ -246,15 +248,15 @@ class HprLib:
             raise RuntimeError("hprlp_b200_scale_only failed")
         return o
 
-    def solve_batched(self, model, C_, AL, AU, l, u, obj_constants=None, param=None):
+    def solve_batched(self, model, C_, AL, AU, l, u, obj_constants=None, param=None, n_gpus=None):
         """Dense inputs column-major: arrays of shape (B, n) / (B, m) in C order == n x B column-major."""
         mm = model.contents
         m, n = mm.m, mm.n
         C_, AL, AU, l, u = (_f64(a) for a in (C_, AL, AU, l, u))
         B = C_.shape[0]
         oc = _f64(obj_constants) if obj_constants is not None else None
-        res = self.lib.solve_batched(model, B, _dp(C_), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(oc),
-                                     C.byref(param) if param is not None else None)
+        args = (model, B, _dp(C_), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(oc), C.byref(param) if param is not None else None)
+        res = self.lib.solve_batched(*args) if n_gpus is None else self.lib.hprlp_b200_solve_batched_multi(*args, int(n_gpus))
         out = dict(m=res.m, n=res.n, batch_size=res.batch_size, time=res.time, setup_time=res.setup_time,
                    solve_time=res.solve_time, power_time=res.power_time)
         if res.status:
@@ -413,3 +415,38 @@ TOY_LP = dict(m=2, n=2, rowPtr=np.array([0, 2, 4], np.int32), colIndex=np.array(
               values=np.array([1.0, 2.0, 3.0, 1.0]), AL=np.array([-np.inf, -np.inf]), AU=np.array([10.0, 12.0]),
               l=np.zeros(2), u=np.full(2, np.inf), c=np.array([-3.0, -5.0]))
 """The toy LP of every reference example (examples/cpp/example_direct_lp.cpp:14): x*=(2.8,3.6), obj=-26.4."""
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-process batch sharding helpers (bench.py under torchrun; tests/test_multi_cpu.py with gloo)
+# ---------------------------------------------------------------------------------------------
+def shard_range(B, world, rank):
+    """Contiguous instance shard of rank `rank` -- the same split hprlp_b200_solve_batched_multi uses."""
+    base, rem = divmod(int(B), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_shards(dist, local, B, world, rank):
+    """All-gather per-rank result rows (shape (shard, k)) into the (B, k) array in instance order."""
+    import torch
+    k = int(local.shape[1])
+    sizes = [shard_range(B, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    buf = torch.zeros((width, k), dtype=torch.float64, device=dev)
+    buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return np.concatenate([outs[r][: hi - lo].cpu().numpy() for r, (lo, hi) in enumerate(sizes)], axis=0)
+
+
+def reduce_time_units(dist, ms, units):
+    """Timing contract of bench.py: max over ranks of the device time, sum over ranks of the processed units."""
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=dev)
+    u = torch.tensor([float(units)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(u.item())

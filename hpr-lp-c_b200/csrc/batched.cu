@@ -25,7 +25,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/batched_solver.h"
@@ -533,13 +535,13 @@ void check_restart(RestartHost *r, int iter, int check_iter, const std::vector<u
 
 using namespace hpr;
 
-extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
-                                                const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in, const HPRLP_FLOAT *l_in,
-                                                const HPRLP_FLOAT *u_in, const HPRLP_FLOAT *obj_constants,
-                                                const HPRLP_parameters *param) {
-    if (!model || !model->A || batch_size <= 0 || !C_in || !AL_in || !AU_in || !l_in || !u_in) {
-        return make_batched_error("ERROR", model ? model->m : 0, model ? model->n : 0, std::max(batch_size, 0));
-    }
+extern "C" void free_batched_results(HPRLP_batched_results *results);
+
+// One GPU: the whole batch on device param->device_number.
+static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
+                                                     const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in, const HPRLP_FLOAT *l_in,
+                                                     const HPRLP_FLOAT *u_in, const HPRLP_FLOAT *obj_constants,
+                                                     const HPRLP_parameters *param) {
     HPRLP_parameters def;
     HPRLP_parameters actual = param ? *param : def;
     actual.use_presolve = false;
@@ -776,6 +778,89 @@ extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int bat
     out.power_time = power_time;
     out.time = setup_time + solve_time;
     return out;
+}
+
+// Batch sharding over the GPUs of one node: instances are independent, A / scaling / lambda_max are
+// replicated per GPU (deterministic: same cuRAND seed), no per-iteration collective.  One host thread per GPU.
+// Known divergence (documented in DESIGN.md): the reference's shared lambda_max can be bumped by any instance of
+// the batch (src/batched_solver.cu:642-646); here a bump stays local to the shard that saw it.
+extern "C" HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
+                                                                 const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in,
+                                                                 const HPRLP_FLOAT *l_in, const HPRLP_FLOAT *u_in,
+                                                                 const HPRLP_FLOAT *obj_constants, const HPRLP_parameters *param,
+                                                                 int n_gpus) {
+    if (!model || !model->A || batch_size <= 0 || !C_in || !AL_in || !AU_in || !l_in || !u_in) {
+        return make_batched_error("ERROR", model ? model->m : 0, model ? model->n : 0, std::max(batch_size, 0));
+    }
+    int avail = 0;
+    if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) throw std::runtime_error("solve_batched: no CUDA device");
+    HPRLP_parameters def;
+    const HPRLP_parameters base = param ? *param : def;
+    int ng = std::max(1, std::min(std::min(n_gpus, avail), batch_size));
+    if (ng == 1) return solve_batched_on_device(model, batch_size, C_in, AL_in, AU_in, l_in, u_in, obj_constants, &base);
+
+    const int m = model->m, n = model->n, B = batch_size;
+    std::vector<HPRLP_batched_results> parts(ng);
+    std::vector<int> begin(ng + 1, 0);
+    for (int d = 0; d < ng; ++d) begin[d + 1] = begin[d] + B / ng + (d < B % ng ? 1 : 0);   // contiguous shards
+    std::vector<std::thread> workers;
+    std::vector<std::string> errors(ng);
+    for (int d = 0; d < ng; ++d) {
+        workers.emplace_back([&, d]() {
+            try {
+                HPRLP_parameters p = base;
+                p.device_number = base.device_number + d;
+                const int k0 = begin[d], nb = begin[d + 1] - begin[d];
+                parts[d] = solve_batched_on_device(model, nb, C_in + (size_t)k0 * n, AL_in + (size_t)k0 * m, AU_in + (size_t)k0 * m,
+                                                   l_in + (size_t)k0 * n, u_in + (size_t)k0 * n,
+                                                   obj_constants ? obj_constants + k0 : nullptr, &p);
+            } catch (const std::exception &e) {
+                errors[d] = e.what();
+            }
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int d = 0; d < ng; ++d)
+        if (!errors[d].empty()) throw std::runtime_error("solve_batched shard " + std::to_string(d) + ": " + errors[d]);
+    HPRLP_batched_results out;
+    out.m = m; out.n = n; out.batch_size = B;
+    out.x = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    out.y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)m * B));
+    out.z = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    out.primal_obj = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.residuals = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.gap = static_cast<double *>(std::malloc(sizeof(double) * B));
+    out.iter = static_cast<int *>(std::malloc(sizeof(int) * B));
+    out.status = static_cast<char *>(std::calloc(static_cast<size_t>(B) * 64, sizeof(char)));
+    for (int d = 0; d < ng; ++d) {
+        const int k0 = begin[d], nb = begin[d + 1] - begin[d];
+        HPRLP_batched_results &r = parts[d];
+        std::memcpy(out.x + (size_t)k0 * n, r.x, sizeof(double) * (size_t)n * nb);
+        std::memcpy(out.y + (size_t)k0 * m, r.y, sizeof(double) * (size_t)m * nb);
+        std::memcpy(out.z + (size_t)k0 * n, r.z, sizeof(double) * (size_t)n * nb);
+        std::memcpy(out.primal_obj + k0, r.primal_obj, sizeof(double) * nb);
+        std::memcpy(out.residuals + k0, r.residuals, sizeof(double) * nb);
+        std::memcpy(out.gap + k0, r.gap, sizeof(double) * nb);
+        std::memcpy(out.iter + k0, r.iter, sizeof(int) * nb);
+        std::memcpy(out.status + (size_t)64 * k0, r.status, (size_t)64 * nb);
+        out.setup_time = std::max(out.setup_time, r.setup_time);
+        out.solve_time = std::max(out.solve_time, r.solve_time);
+        out.power_time = std::max(out.power_time, r.power_time);
+        free_batched_results(&r);
+    }
+    out.time = out.setup_time + out.solve_time;
+    return out;
+}
+
+// The reference entry point (src/batched_solver.cu:939).  HPRLP_NUM_GPUS=N (environment) shards the batch over N
+// GPUs starting at param->device_number; default 1 = the reference's single-GPU behaviour.
+extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
+                                                const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in, const HPRLP_FLOAT *l_in,
+                                                const HPRLP_FLOAT *u_in, const HPRLP_FLOAT *obj_constants,
+                                                const HPRLP_parameters *param) {
+    int ng = 1;
+    if (const char *e = getenv("HPRLP_NUM_GPUS")) ng = std::max(1, atoi(e));
+    return hprlp_b200_solve_batched_multi(model, batch_size, C_in, AL_in, AU_in, l_in, u_in, obj_constants, param, ng);
 }
 
 extern "C" void free_batched_results(HPRLP_batched_results *results) {   // reference :1094-1105

@@ -59,6 +59,14 @@ int hprlp_b200_scale_only(const LP_info_cpu *model, const HPRLP_parameters *para
                           double *AL, double *AU, double *l, double *u, double *c,
                           double *row_norm, double *col_norm, double *scalars6);
 
+/* solve_batched sharded over n_gpus GPUs of one node (devices param->device_number ... +n_gpus-1): contiguous
+ * instance shards, A replicated, no per-iteration collective.  solve_batched itself calls this with
+ * n_gpus = $HPRLP_NUM_GPUS (default 1).  (new functionality; reference is single-GPU) */
+HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C,
+                                                     const HPRLP_FLOAT *AL, const HPRLP_FLOAT *AU, const HPRLP_FLOAT *l,
+                                                     const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
+                                                     const HPRLP_parameters *param, int n_gpus);
+
 /* cudaProfilerStart/Stop of the library's (statically linked) CUDA runtime: lets `ncu --profile-from-start off`
  * capture only the timed region of bench.py. */
 void hprlp_b200_profiler_start(void);
