@@ -175,6 +175,9 @@ static inline int vec_grid(int len) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+// per-CTA partial blocks written by one streamed pass: main-kernel CTAs + fix-up CTAs
+static int part_blocks(const DevCsr &M) { return M.n_items + (M.n_items * kWarps + kThreads - 1) / kThreads; }
+
 static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
@@ -183,25 +186,45 @@ static CsrView<int> view_of(const DevCsr &M) {
     return v;
 }
 
+static thread_local long long g_fixup_launches = 0;   // fix-up launches issued by launch_one (added to Engine::launches)
+
+template <class Op, int G>
+static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
+    constexpr size_t bytes = stream_smem_bytes<Op>();
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (const char *e = getenv("HPRLP_CARVEOUT"))   // tuning hook: shared-memory carve-out in percent
+            HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        configured = true;
+    }
+    csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
+    // rows cut by item boundaries: summed in item order + epilogue (stream order makes the partials visible)
+    const int n_real = (int)((v.nnz + kWarpChunk - 1) / kWarpChunk);
+    const int n_fix = (v.n_items * kWarps + kThreads - 1) / kThreads;
+    csr_fixup_kernel<Op, int><<<n_fix, kThreads, 0, st>>>(v, op, n_real, v.n_items);
+    g_fixup_launches++;
+}
+
 template <class Op>
 static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
     const CsrView<int> v = view_of(M);
     switch (M.G) {
-        case 1:  csr_stream_kernel<Op, 1, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
-        case 2:  csr_stream_kernel<Op, 2, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
-        case 4:  csr_stream_kernel<Op, 4, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
-        case 8:  csr_stream_kernel<Op, 8, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
-        case 16: csr_stream_kernel<Op, 16, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
-        default: csr_stream_kernel<Op, 32, int><<<M.n_items, kThreads, 0, st>>>(v, op); break;
+        case 1:  launch_one<Op, 1>(v, op, st); break;
+        case 2:  launch_one<Op, 2>(v, op, st); break;
+        case 4:  launch_one<Op, 4>(v, op, st); break;
+        case 8:  launch_one<Op, 8>(v, op, st); break;
+        case 16: launch_one<Op, 16>(v, op, st); break;
+        default: launch_one<Op, 32>(v, op, st); break;
     }
 }
 // setup / check-iteration passes: fewer instantiations
 template <class Op>
 static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
     const CsrView<int> v = view_of(M);
-    if (M.G <= 2)      csr_stream_kernel<Op, 1, int><<<M.n_items, kThreads, 0, st>>>(v, op);
-    else if (M.G <= 8) csr_stream_kernel<Op, 4, int><<<M.n_items, kThreads, 0, st>>>(v, op);
-    else               csr_stream_kernel<Op, 16, int><<<M.n_items, kThreads, 0, st>>>(v, op);
+    if (M.G <= 2)      launch_one<Op, 1>(v, op, st);
+    else if (M.G <= 8) launch_one<Op, 4>(v, op, st);
+    else               launch_one<Op, 16>(v, op, st);
 }
 
 template <typename T>
@@ -249,10 +272,11 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.rowPtr = dalloc<int>((size_t)rows + 1);
     M.col = dalloc<int>(padded);
     M.val = dalloc<double>(padded);
-    M.item_row = dalloc<int>((size_t)M.n_items + 1);
-    M.head_part = dalloc<double>((size_t)M.n_items * 2);
-    M.tail_part = dalloc<double>((size_t)M.n_items * 2);
-    M.counters = dalloc<unsigned>((size_t)M.n_items);
+    const size_t witems = (size_t)M.n_items * kWarps;   // warp items (n_items = CTAs)
+    M.item_row = dalloc<int>(witems + 1);
+    M.head_part = dalloc<double>(witems * 2);
+    M.tail_part = dalloc<double>(witems * 2);
+    M.counters = dalloc<unsigned>(witems);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
@@ -276,7 +300,8 @@ static int pick_lanes(double mean_len, const char *env_name) {
 
 void Engine::finish_matrix(DevCsr &M) {
     const int threads = 256;
-    build_item_rows_kernel<int><<<(M.n_items + 1 + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.n_items, M.item_row);
+    const int entries = M.n_items * kWarps + 1;
+    build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
 }
@@ -289,7 +314,7 @@ void Engine::alloc_common() {
     row_norm = dalloc<double>(m); col_norm = dalloc<double>(n);
     d_params = dalloc<double>(4);
     d_k = dalloc<int>(2);
-    partial_blocks = std::max(std::max(A.n_items, AT.n_items), kVecBlocks);
+    partial_blocks = std::max(std::max(part_blocks(A), part_blocks(AT)), kVecBlocks);
     d_partials = dalloc<double>((size_t)partial_blocks * kMaxSlots);
     d_scal = dalloc<double>(16);
     HPR_CUDA_CHECK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
@@ -473,7 +498,7 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
         launch_stream(AT, o1, stream);
         SpmvOp<true> o2; o2.g = atq; o2.out = z; o2.q = q; o2.partials = d_partials;
         launch_stream(A, o2, stream);
-        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 2, d_scal);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
         launches += 4;
         if (it % 10 == 0) {
             power_error_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, q, d_scal + 1, m, d_partials);
@@ -549,16 +574,17 @@ void Engine::run_normal(int count) {
                 cudaGraph_t g = nullptr;
                 cudaGraphExec_t ge = nullptr;
                 HPR_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                const long long before = launches;
+                const long long before = launches, before_fix = g_fixup_launches;
                 for (int i = 0; i < len; ++i) launch_iteration(false);
                 launches = before;
+                g_fixup_launches = before_fix;
                 HPR_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
                 HPR_CUDA_CHECK(cudaGraphInstantiate(&ge, g, nullptr, nullptr, 0));
                 cudaGraphDestroy(g);
                 it = graphs_.emplace(len, ge).first;
             }
             HPR_CUDA_CHECK(cudaGraphLaunch(it->second, stream));
-            launches += 2LL * len;
+            launches += 4LL * len;
         }
         count -= len;
     }
@@ -573,14 +599,14 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     if (iter == 0) { ResidualDualOp<false, true> o; fill_dual(o); launch_stream(AT, o, stream); }
     else if (compute_gap) { ResidualDualOp<true, false> o; fill_dual(o); launch_stream(AT, o, stream); }
     else { ResidualDualOp<false, false> o; fill_dual(o); launch_stream(AT, o, stream); }
-    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, AT.n_items, 5, d_scal);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(AT), 5, d_scal);
     auto fill_primal = [&](auto &o) {
         o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
         o.y_bar = y_bar; o.y_tmp = y_tmp; o.partials = d_partials;
     };
     if (compute_gap) { ResidualPrimalOp<true> o; fill_primal(o); launch_stream(A, o, stream); }
     else { ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream); }
-    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 4, d_scal + 5);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 4, d_scal + 5);
     launches += 4;
     fetch_scalars(9);
     HPR_CUDA_CHECK(cudaGetLastError());
@@ -615,7 +641,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
 double Engine::weighted_norm_after_restart() {
     WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
     launch_stream(A, o, stream);
-    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, A.n_items, 2, d_scal);
+    final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp, n, d_partials);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
     launches += 4;
@@ -895,7 +921,7 @@ void Engine::fill_hooks(SolveHooks *hooks) {
     hooks->lambda_max = lambda_max;
     hooks->sigma = sigma;
     hooks->restarts = loop.rs.times;
-    hooks->kernel_launches = launches;
+    hooks->kernel_launches = launches + g_fixup_launches;
     hooks->scal[0] = b_scale; hooks->scal[1] = c_scale; hooks->scal[2] = norm_b; hooks->scal[3] = norm_c;
     hooks->scal[4] = norm_b_org; hooks->scal[5] = norm_c_org;
 }

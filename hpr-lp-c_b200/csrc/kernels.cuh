@@ -2,19 +2,23 @@
 //
 // One streaming skeleton, `csr_stream_kernel`, carries every pass over a CSR matrix (the two
 // fused HPR phases, the KKT residual passes, power iteration, Ruiz/Pock-Chambolle/Curtis-Reid
-// row statistics).  It is an nnz-balanced ("merge-style") CSR-stream kernel:
+// row statistics).  It is an nnz-balanced ("merge-style") CSR-stream kernel at WARP granularity:
 //
-//   item  = a fixed chunk of kChunk consecutive nonzeros (one CTA per item, grid = nnz/kChunk),
-//           so the work per CTA is identical whatever the row-length distribution is
-//           (power-law rows included; no row-id lists, no short/long buckets).
-//   phase 1  every thread streams its nonzeros with 128-bit/64-bit coalesced loads
-//           (double2 values, int2 column indices, evict-first), gathers the dense vector through
-//           the read-only path (stays L2 resident) and stores the products in shared memory.
-//   phase 2  G lanes per row (G chosen per matrix from the mean row length) sum the row's slice
-//           of the product array; lane 0 runs the fused epilogue (projection, dual update,
-//           Halpern averaging, residual terms ...).
+//   item  = a fixed chunk of kWarpChunk (512) consecutive nonzeros owned by ONE WARP, so the work
+//           per warp is identical whatever the row-length distribution is (power-law rows
+//           included; no row-id lists, no short/long buckets) and warps never wait on each other:
+//           there is no CTA barrier on the path, every warp of an SM is at a different point of
+//           its item, which is what hides the HBM/L2 latency of the gathers (r1 v1 used CTA-wide
+//           items + __syncthreads and was latency-bound: profiles/r1_v1_ncu_full_c2_details.txt).
+//   phase 1  the warp streams its nonzeros with 128-bit/64-bit coalesced loads (double2 values,
+//           int2 column indices, evict-first), gathers the dense vector through the read-only path
+//           (L2 resident) and stores the products in its private slice of shared memory.
+//   phase 2  G lanes per row (G chosen per matrix from the mean row length) sum the row's slice of
+//           the product array; the row totals are handed to one lane per row, so that the fused
+//           epilogue (projection, dual update, Halpern averaging, residual terms ...) runs
+//           lane-parallel over consecutive rows with coalesced vector loads/stores.
 //   rows cut by an item boundary publish a partial sum; the last contributor to arrive (one
-//           atomic counter per row end) adds the partials in item order and runs the epilogue --
+//           atomic counter per row end) adds the partials in a fixed order and runs the epilogue --
 //           deterministic, and no second "fix-up" launch.
 //
 // Replaces, on the iteration path, the reference's fused_update_* kernels
@@ -29,9 +33,22 @@
 namespace hpr {
 
 constexpr int kThreads = 256;
-constexpr int kPerThread = 8;
-constexpr int kChunk = kThreads * kPerThread;  // nonzeros per item
-constexpr int kMaxSlots = 8;                   // reduction slots per CTA
+constexpr int kWarps = kThreads / 32;
+#ifndef HPR_LANE_NNZ
+#define HPR_LANE_NNZ 8
+#endif
+#ifndef HPR_ROUND_NNZ
+#define HPR_ROUND_NNZ 8
+#endif
+#ifndef HPR_MIN_BLOCKS
+#define HPR_MIN_BLOCKS 8
+#endif
+constexpr int kLaneNnz = HPR_LANE_NNZ;          // nonzeros per lane per item
+constexpr int kRoundNnz = HPR_ROUND_NNZ;        // nonzeros per lane per load round (loads in flight)
+constexpr int kWarpChunk = 32 * kLaneNnz;       // nonzeros per warp item
+constexpr int kChunk = kWarps * kWarpChunk;     // nonzeros per CTA (array padding granularity)
+constexpr int kMaxSlots = 8;                    // reduction slots per CTA
+constexpr int kSeqPartials = 8;                 // split rows with more partials are summed by the whole warp
 
 template <typename RP>
 struct CsrView {
@@ -40,11 +57,11 @@ struct CsrView {
     const RP *rowPtr;
     const int *col;       // padded to a multiple of kChunk (pad: col 0, value 0)
     const double *val;    // padded likewise
-    const int *item_row;  // n_items + 1 entries: first row finalised by item i
-    int n_items;
-    double *head_part;    // [n_items * 2] partial of the row entering the item from the left
-    double *tail_part;    // [n_items * 2] partial of the row leaving the item to the right
-    unsigned *counters;   // [n_items] arrivals per split row (indexed by the item where the row ends)
+    const int *item_row;  // n_ctas*kWarps + 1 entries: first row finalised by warp item i
+    int n_items;          // CTAs in the grid
+    double *head_part;    // [items * 2] partial of the row entering the item from the left
+    double *tail_part;    // [items * 2] partial of the row leaving the item to the right
+    unsigned *counters;   // [items] arrivals per split row (indexed by the item where the row ends)
 };
 
 __device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
@@ -54,7 +71,9 @@ __device__ __forceinline__ int2 ld_stream(const int2 *p) { return __ldcs(p); }
 // out[blockIdx.x * kMaxSlots + s].  The caller's final_reduce_kernel adds the per-CTA values
 // in block order, so every reduction is run-to-run reproducible.
 template <int NS>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double *out, double *scratch /* >= 8*NS doubles */) {
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double *out, double *scratch /* >= 8*NS doubles */,
+                                                   int block = -1) {
+    if (block < 0) block = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -68,9 +87,12 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double *ou
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) v += scratch[threadIdx.x * (kThreads / 32) + w];
-        out[(size_t)blockIdx.x * kMaxSlots + threadIdx.x] = v;
+        out[(size_t)block * kMaxSlots + threadIdx.x] = v;
     }
 }
+
+template <bool MAX>
+__device__ __forceinline__ double combine(double a, double b) { return MAX ? fmax(a, b) : a + b; }
 
 // ------------------------------------------------------------------------------------------------
 // The streaming skeleton.  Op supplies:
@@ -80,138 +102,144 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double *ou
 //   void elem(v, col, out[NV])   per-nonzero term
 //   void row(r, acc[NV], p0, p1) fused epilogue of a complete row
 //   void finish(scratch)         CTA-level reductions (may be empty)
+// Dynamic shared memory: kWarps * NV * kWarpChunk doubles (product slices) + reduction scratch.
 // ------------------------------------------------------------------------------------------------
+template <class Op>
+constexpr size_t stream_smem_bytes() {
+    return sizeof(double) * ((size_t)kWarps * Op::NV * kWarpChunk + (size_t)kMaxSlots * kWarps);
+}
+
 template <class Op, int G, typename RP>
-__global__ void __launch_bounds__(kThreads, 4) csr_stream_kernel(CsrView<RP> M, Op op) {
+__global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(CsrView<RP> M, Op op) {
     constexpr int NV = Op::NV;
-    __shared__ __align__(16) double prod[NV][kChunk];
-    __shared__ double red_scratch[kMaxSlots * (kThreads / 32)];
+    constexpr bool MX = Op::kMax;
+    constexpr int RPR = 32 / G;   // rows per reduce round
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *prod = smem + (size_t)warp * NV * kWarpChunk;            // [NV][kWarpChunk], private to this warp
+    double *red_scratch = smem + (size_t)kWarps * NV * kWarpChunk;
 
     op.init();
-    const long long s = (long long)blockIdx.x * kChunk;
-    const long long e = (s + kChunk < M.nnz) ? s + kChunk : M.nnz;
+    const int item = blockIdx.x * kWarps + warp;
+    const long long s = (long long)item * kWarpChunk;
+    const long long e = (s + kWarpChunk < M.nnz) ? s + kWarpChunk : (s < M.nnz ? M.nnz : s);
 
-    // ---- phase 1: stream nonzeros, gather, multiply ------------------------------------------------
+    // row metadata of the first batch: requested before the nonzeros so its latency overlaps phase 1
+    const int rA = __ldg(M.item_row + item);
+    const int rB = __ldg(M.item_row + item + 1);
+    const int r_last = (rB < M.rows) ? rB : M.rows - 1;   // last row touched (rB included: it may start here)
+    long long p0 = 0, p1 = 0;
+    if (rA + lane <= r_last) {
+        p0 = (long long)M.rowPtr[rA + lane];
+        p1 = (long long)M.rowPtr[rA + lane + 1];
+    }
+
+    // ---- phase 1: stream nonzeros, gather, multiply (kRoundNnz loads in flight per lane) -----------
     {
         const double2 *v2 = reinterpret_cast<const double2 *>(M.val + s);
         const int2 *c2 = reinterpret_cast<const int2 *>(M.col + s);
-        double2 vv[kPerThread / 2];
-        int2 cc[kPerThread / 2];
 #pragma unroll
-        for (int u = 0; u < kPerThread / 2; ++u) {
-            cc[u] = ld_stream(c2 + u * kThreads + threadIdx.x);
-            vv[u] = ld_stream(v2 + u * kThreads + threadIdx.x);
-        }
+        for (int rd = 0; rd < kLaneNnz / kRoundNnz; ++rd) {
+            double2 vv[kRoundNnz / 2];
+            int2 cc[kRoundNnz / 2];
 #pragma unroll
-        for (int u = 0; u < kPerThread / 2; ++u) {
-            double o0[NV], o1[NV];
-            op.elem(vv[u].x, cc[u].x, o0);
-            op.elem(vv[u].y, cc[u].y, o1);
-            const int t = u * kThreads + threadIdx.x;
+            for (int u = 0; u < kRoundNnz / 2; ++u) {
+                const int t = (rd * (kRoundNnz / 2) + u) * 32 + lane;
+                cc[u] = ld_stream(c2 + t);
+                vv[u] = ld_stream(v2 + t);
+            }
 #pragma unroll
-            for (int q = 0; q < NV; ++q)
-                *reinterpret_cast<double2 *>(&prod[q][2 * t]) = make_double2(o0[q], o1[q]);
+            for (int u = 0; u < kRoundNnz / 2; ++u) {
+                double o0[NV], o1[NV];
+                op.elem(vv[u].x, cc[u].x, o0);
+                op.elem(vv[u].y, cc[u].y, o1);
+                const int t = (rd * (kRoundNnz / 2) + u) * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < NV; ++q)
+                    *reinterpret_cast<double2 *>(prod + q * kWarpChunk + 2 * t) = make_double2(o0[q], o1[q]);
+            }
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase 2: per-row sums + fused epilogue ------------------------------------------------------
-    const int rA = M.item_row[blockIdx.x];
-    const int rB = M.item_row[blockIdx.x + 1];
-    const int lane = threadIdx.x & 31;
-    const int gl = threadIdx.x & (G - 1);
-    const int gid = threadIdx.x / G;
-    constexpr int NGRP = kThreads / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-
-    for (int base = rA; base <= rB; base += NGRP) {
-        const int r = base + gid;
-        const bool valid = (r <= rB) && (r < M.rows);
-        long long p0 = 0, p1 = 0;
+    // ---- phase 2: row sums (G lanes per row) handed to one lane per row, lane-parallel epilogue ------
+    for (int base = rA; base <= r_last; base += 32) {   // warp-uniform
+        const int r = base + lane;
+        const bool valid = r <= r_last;
+        if (base != rA) {
+            p0 = 0; p1 = 0;
+            if (valid) { p0 = (long long)M.rowPtr[r]; p1 = (long long)M.rowPtr[r + 1]; }
+        }
         int lo = 0, hi = 0;
         if (valid) {
-            p0 = (long long)M.rowPtr[r];
-            p1 = (long long)M.rowPtr[r + 1];
             const long long a = p0 > s ? p0 : s;
             const long long b = p1 < e ? p1 : e;
             if (b > a) { lo = (int)(a - s); hi = (int)(b - s); }
         }
-        double acc[NV];
+        const int nrows = min(32, r_last - base + 1);
+        double tot[NV];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) acc[q] = 0.0;   // |a| >= 0, so 0 is also the identity of fmax here
-        for (int k = lo + gl; k < hi; k += G) {
+        for (int q = 0; q < NV; ++q) tot[q] = 0.0;   // |a| >= 0, so 0 is also the identity of fmax here
+        if (G == 1) {
+            for (int k = lo; k < hi; ++k) {
 #pragma unroll
-            for (int q = 0; q < NV; ++q) acc[q] = Op::kMax ? fmax(acc[q], prod[q][k]) : acc[q] + prod[q][k];
-        }
+                for (int q = 0; q < NV; ++q) tot[q] = combine<MX>(tot[q], prod[q * kWarpChunk + k]);
+            }
+        } else {
+            const int gl = lane & (G - 1), gid = lane / G;
+            const int rounds = (nrows + RPR - 1) / RPR;
+            for (int t = 0; t < rounds; ++t) {
+                const int o = t * RPR + gid;   // row (offset in the batch) reduced by my group this round
+                const int glo = __shfl_sync(0xffffffffu, lo, o);
+                const int ghi = __shfl_sync(0xffffffffu, hi, o);
+                double acc[NV];
 #pragma unroll
-        for (int off = G / 2; off > 0; off >>= 1) {
+                for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+                for (int k = glo + gl; k < ghi; k += G) {
 #pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const double o = __shfl_xor_sync(gmask, acc[q], off);
-                acc[q] = Op::kMax ? fmax(acc[q], o) : acc[q] + o;
+                    for (int q = 0; q < NV; ++q) acc[q] = combine<MX>(acc[q], prod[q * kWarpChunk + k]);
+                }
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) acc[q] = combine<MX>(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], off));
+                }
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const double v = __shfl_sync(0xffffffffu, acc[q], (lane % RPR) * G);
+                    if (lane / RPR == t) tot[q] = v;   // lane L owns row L of the batch
+                }
             }
         }
-        if (!valid) continue;   // whole group leaves together (r is group-uniform)
 
-        const bool head = (r == rA) && (p0 < s);   // row entered this item from the left
-        const bool cont = (p1 > e);                // row continues to the right
-        if (!head && !cont) {
-            if (gl == 0) op.row(r, acc, p0, p1);
-            continue;
-        }
-        if (!head && p0 >= e) continue;            // r == rB but it starts in a later item
-        // ---- split row: publish the partial, last arriver finalises -----------------------------
-        const int ia = (int)(p0 / kChunk);
-        const int ib = (int)((p1 - 1) / kChunk);
-        int last = 0;
-        if (gl == 0) {
-            double *slot = (head ? M.head_part : M.tail_part) + (size_t)blockIdx.x * 2;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) slot[q] = acc[q];
-            __threadfence();
-            const unsigned old = atomicAdd(&M.counters[ib], 1u);
-            last = (old == (unsigned)(ib - ia));
-        }
-        last = __shfl_sync(gmask, last, lane & ~(G - 1));
-        if (last) {
-            __threadfence();
-            double tot[NV];
-#pragma unroll
-            for (int q = 0; q < NV; ++q) tot[q] = 0.0;
-            for (int k = ia + gl; k <= ib; k += G) {
-                const double *src = ((k == ia) ? M.tail_part : M.head_part) + (size_t)k * 2;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const double pv = __ldcg(src + q);
-                    tot[q] = Op::kMax ? fmax(tot[q], pv) : tot[q] + pv;
-                }
-            }
-#pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const double o = __shfl_xor_sync(gmask, tot[q], off);
-                    tot[q] = Op::kMax ? fmax(tot[q], o) : tot[q] + o;
-                }
-            }
-            if (gl == 0) {
-                M.counters[ib] = 0u;   // re-arm for the next launch
+        // lane-parallel epilogue.  Rows cut by an item boundary only publish their partial sum here (plain
+        // stores, no fence, no atomic); csr_fixup_kernel, launched right after on the same stream, adds the
+        // partials of each cut row in item order and runs its epilogue -- deterministic by construction.
+        if (valid) {
+            const bool head = (r == rA) && (p0 < s);   // row entered this item from the left
+            const bool cont = (p1 > e);                // row continues to the right
+            if (!head && !cont) {
                 op.row(r, tot, p0, p1);
+            } else if (head || p0 < e) {               // (else: r == rB and it starts in a later item)
+                double *slot = (head ? M.head_part : M.tail_part) + (size_t)item * 2;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) slot[q] = tot[q];
             }
         }
     }
-    op.finish(red_scratch);
+    op.finish(red_scratch, blockIdx.x);
 }
 
-// first row finalised by item i = first r with rowPtr[r+1] > i*kChunk (item 0 also owns leading
-// empty rows, item n_items-1 the trailing ones).
+// item_row[i] = first row finalised by warp item i = first r with rowPtr[r+1] > i*kWarpChunk (item 0 also owns
+// leading empty rows; items at or beyond the last real one get `rows`, so the last real item owns trailing
+// empty rows and pure padding items own nothing).
 template <typename RP>
-__global__ void build_item_rows_kernel(const RP *rowPtr, int rows, int n_items, int *item_row) {
+__global__ void build_item_rows_kernel(const RP *rowPtr, int rows, long long nnz, int n_entries, int *item_row) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n_items) return;
+    if (i >= n_entries) return;
     if (i == 0) { item_row[0] = 0; return; }
-    if (i == n_items) { item_row[i] = rows; return; }
-    const long long target = (long long)i * kChunk;
+    const long long target = (long long)i * kWarpChunk;
+    if (target >= nnz) { item_row[i] = rows; return; }
     int lo = 0, hi = rows;
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
@@ -220,8 +248,69 @@ __global__ void build_item_rows_kernel(const RP *rowPtr, int rows, int n_items, 
     item_row[i] = lo;
 }
 
-// Sum the per-CTA partials (block order) into out[0..ns): one CTA, fixed tree => deterministic.
-__global__ void final_reduce_kernel(const double *partials, int n_blocks, int ns, double *out);
+
+// Finalises the rows cut by item boundaries: candidate i = warp item i whose first row entered from the left and
+// ends inside it.  total = tail[ia] + head[ia+1] + ... + head[i] (item order); rows with more than kSeqPartials
+// partials are summed by the whole warp (stride-32 order + xor tree).  One candidate per lane, so the epilogue
+// loads of neighbouring cut rows are issued together.  Partial-sum blocks of reducing ops go to
+// partials[(block_offset + blockIdx.x)].
+template <class Op, typename RP>
+__global__ void __launch_bounds__(kThreads) csr_fixup_kernel(CsrView<RP> M, Op op, int n_real_items, int block_offset) {
+    constexpr int NV = Op::NV;
+    constexpr bool MX = Op::kMax;
+    __shared__ double red_scratch[kMaxSlots * kWarps];
+    const int lane = threadIdx.x & 31;
+    op.init();
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    int coop = 0, ia = 0, r = 0;
+    long long p0 = 0, p1 = 0;
+    if (i > 0 && i < n_real_items) {
+        r = __ldg(M.item_row + i);
+        const int rnext = __ldg(M.item_row + i + 1);
+        if (r < M.rows && rnext > r) {                       // row r is finalised by item i
+            p0 = (long long)M.rowPtr[r];
+            p1 = (long long)M.rowPtr[r + 1];
+            const long long s = (long long)i * kWarpChunk;
+            if (p0 < s) {                                     // ... and it entered from the left: a cut row
+                ia = (int)(p0 / kWarpChunk);
+                if (i - ia < kSeqPartials) {
+                    double sum[NV];
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) sum[q] = M.tail_part[(size_t)ia * 2 + q];
+                    for (int k = ia + 1; k <= i; ++k) {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], M.head_part[(size_t)k * 2 + q]);
+                    }
+                    op.row(r, sum, p0, p1);
+                } else {
+                    coop = 1;
+                }
+            }
+        }
+    }
+    unsigned pend = __ballot_sync(0xffffffffu, coop);
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        const int a = __shfl_sync(0xffffffffu, ia, src);
+        const int b = __shfl_sync(0xffffffffu, i, src);
+        double sum[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sum[q] = 0.0;
+        for (int k = a + lane; k <= b; k += 32) {
+            const double *srcp = ((k == a) ? M.tail_part : M.head_part) + (size_t)k * 2;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], srcp[q]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
+        }
+        if (lane == src) op.row(r, sum, p0, p1);
+        pend &= pend - 1;
+    }
+    op.finish(red_scratch, block_offset + blockIdx.x);
+}
 
 // ================================================================================================
 // Ops
@@ -230,7 +319,7 @@ struct OpBase {
     static constexpr int NV = 1;
     static constexpr bool kMax = false;
     __device__ __forceinline__ void init() {}
-    __device__ __forceinline__ void finish(double *) {}
+    __device__ __forceinline__ void finish(double *, int) {}
 };
 
 // x-phase (reference fused_update_x_z_rows_*_kernel, HPR_cuda_kernels.cu:297-361; check variant
@@ -335,7 +424,7 @@ struct ResidualDualOp : OpBase {
             t[4] += q * q;
         }
     }
-    __device__ __forceinline__ void finish(double *scratch) { block_reduce_store<5>(t, partials, scratch); }
+    __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<5>(t, partials, scratch, block); }
 };
 
 // Primal residual pass over A (reference residual_compute_Rp_cusparse, src/main_iterate.cu:207-215,
@@ -361,7 +450,7 @@ struct ResidualPrimalOp : OpBase {
         t[1] += y_obj[i] * y_bar[i];
         if (GAP) { const double dy = y_tmp[i]; t[2] += acc[NV - 1] * dy; t[3] += dy * dy; }
     }
-    __device__ __forceinline__ void finish(double *scratch) { block_reduce_store<4>(t, partials, scratch); }
+    __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<4>(t, partials, scratch, block); }
 };
 
 // M-norm cross term after a restart iteration (reference compute_weighted_norm,
@@ -377,7 +466,7 @@ struct WeightedNormOp : OpBase {
         t[0] += acc[0] * d;
         t[1] += d * d;
     }
-    __device__ __forceinline__ void finish(double *scratch) { block_reduce_store<2>(t, partials, scratch); }
+    __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<2>(t, partials, scratch, block); }
 };
 
 // Plain SpMV out = M * g, with optional fused <out,out> and <q,out> (power iteration,
@@ -395,8 +484,8 @@ struct SpmvOp : OpBase {
         out[i] = acc[0];
         if (DOTS) { t[0] += acc[0] * acc[0]; t[1] += q[i] * acc[0]; }
     }
-    __device__ __forceinline__ void finish(double *scratch) {
-        if (DOTS) block_reduce_store<2>(t, partials, scratch);
+    __device__ __forceinline__ void finish(double *scratch, int block) {
+        if (DOTS) block_reduce_store<2>(t, partials, scratch, block);
     }
 };
 
@@ -432,8 +521,8 @@ struct CurtisReidOp : OpBase {
 // operations in the reference's order (mul_CSR_A_row then mul_CSR_AT_row, HPR_cuda_kernels.cu:122-157;
 // call order src/scaling.cu:72-76,136-141): for A   first = rowfac[row],  second = gathfac[col];
 //                                           for A^T first = gathfac[col], second = rowfac[row].
-// Same item decomposition as csr_stream_kernel: row factors are expanded into shared memory by the
-// row owners, then the nnz-parallel phase is fully coalesced.
+// CTA-level items (kChunk nonzeros = kWarps warp items): row factors are expanded into shared memory by
+// the row owners, then the nnz-parallel phase is fully coalesced.
 // ------------------------------------------------------------------------------------------------
 template <bool DIVIDE, bool ROW_FIRST, typename RP>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -441,8 +530,8 @@ scale_values_kernel(CsrView<RP> M, double *val_rw, const double *rowfac, const d
     __shared__ double rf[kChunk];
     const long long s = (long long)blockIdx.x * kChunk;
     const long long e = (s + kChunk < M.nnz) ? s + kChunk : M.nnz;
-    const int rA = M.item_row[blockIdx.x];
-    const int rB = M.item_row[blockIdx.x + 1];
+    const int rA = M.item_row[blockIdx.x * kWarps];
+    const int rB = M.item_row[(blockIdx.x + 1) * kWarps];
     constexpr int GG = 8;
     const int gl = threadIdx.x & (GG - 1);
     const int gid = threadIdx.x / GG;
