@@ -45,6 +45,10 @@ WORKLOADS = {
     "c3": dict(kind="powerlaw", m=2_000_000, n=5_000_000, nnz=100_000_000,
                name="configs[2]: synthetic power-law LP m=2e6 n=5e6 nnz=1e8, tol 1e-4"),
     "small": dict(kind="uniform", m=5_000, n=20_000, nnz=200_000, name="debug: uniform m=5e3 n=2e4 nnz=2e5"),
+    # BASELINE.json configs[3]: solve_batched shared-A m=5e4 n=2e5 nnz=2e6, batch 256, batch-sharded over the GPUs
+    "c4": dict(kind="uniform", m=50_000, n=200_000, nnz=2_000_000, batch=256, iters=300,
+               name="configs[3]: solve_batched shared-A m=5e4 n=2e5 nnz=2e6, batch 256, batch-sharded"),
+    "c4small": dict(kind="uniform", m=2_000, n=8_000, nnz=80_000, batch=64, iters=300, name="debug: batched m=2e3 n=8e3 B=64"),
 }
 
 
@@ -224,6 +228,57 @@ def run_engine_arm(args, pkg, spec, lp, rank, world, local, dist):
     return out
 
 
+def make_batch(pkg, spec, lo, hi):
+    """Shared matrix + instances lo..hi-1 (instance k draws its primal-dual pair with seed+k)."""
+    base = pkg.synth_lp(spec["kind"], spec["m"], spec["n"], spec["nnz"])
+    vs = [pkg.synth_vectors(base, pkg.SEED, pkg.SEED + k) for k in range(lo, hi)]
+    st = lambda key: np.stack([v[key] for v in vs])
+    return base, dict(C=st("c"), AL=st("AL"), AU=st("AU"), l=st("l"), u=st("u"))
+
+
+def run_batched(args, pkg, spec, lib, rank, world, local, dist, impl):
+    """One step = one solve_batched call of `iters` iterations on this rank's contiguous instance shard
+    (A replicated, no data-path collective). value = instance-iterations/s over all ranks, max-over-ranks time."""
+    B = spec["batch"]
+    lo, hi = pkg.shard_range(B, world, rank)
+    base, d = make_batch(pkg, spec, lo, hi)
+    param = pkg.Parameters.default(stop_tol=0.0, max_iter=spec["iters"], use_presolve=False, device_number=local)
+    model = lib.create_model(base)
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    times, walls = [], []
+    barrier(dist, local)
+    with ClockSampler(local) as clk:
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            r = lib.solve_batched(model, d["C"], d["AL"], d["AU"], d["l"], d["u"], None, param)
+            w = time.perf_counter() - t0
+            if i >= warm:
+                times.append(r["solve_time"]); walls.append(w)
+    barrier(dist, local)
+    lib.free_model(model)
+    n_inst_iters = (hi - lo) * spec["iters"]
+    t_solve, units = reduce_max_sum(dist, local, 1e3 * min(times), n_inst_iters)
+    t_wall, _ = reduce_max_sum(dist, local, 1e3 * min(walls), 0)
+    if rank != 0:
+        return None
+    m, n, nnz = base["m"], base["n"], int(base["values"].shape[0])
+    bytes_iter = 24 * nnz + 4 * (n + m) + B * (64 * n + 48 * m)    # SURVEY.md 8(d), whole batch, A streamed once
+    out = dict(metric="HPR instance-iterations/s, solve_batched shared-A", value=units / (t_solve * 1e-3), unit="instance-iterations/s",
+               n_gpus=world, steps=steps, warmup=warm, ms_per_step=t_solve, higher_is_better=True, scaling="strong", vs_baseline=None,
+               dtype="f64", data="synthetic", impl=impl,
+               config=dict(workload=spec["name"], m=m, n=n, nnz=nnz, batch=B, iters_per_step=spec["iters"],
+                           parallelism="batch-sharded dp%d, A replicated, no collective" % world,
+                           l2="batched vectors %.0f MB >> 126 MB L2" % (B * (64 * n + 48 * m) / 1e6)),
+               e2e=dict(value=units / (t_wall * 1e-3), unit="instance-iterations/s",
+                        h2d_bytes_per_step=8 * (hi - lo) * (3 * n + 2 * m) + 24 * nnz, d2h_bytes_per_step=8 * (hi - lo) * (2 * n + m)),
+               roofline=dict(bound="hbm", achieved=bytes_iter * spec["iters"] / (t_solve * 1e-3) / 1e9 / world, peak=6549.1, unit="GB/s",
+                             frac=bytes_iter * spec["iters"] / (t_solve * 1e-3) / 1e9 / world / 6549.1, traffic=None,
+                             note="whole loop (fused SpMM+prox x/y kernels + checks); per GPU; algorithmic bytes 24nnz+4(n+m)+B(64n+48m)"),
+               clocks=clk.summary(), gpu_launches=None)
+    return out
+
+
 def steady_state_rate(pkg, lib, lp, local, k1=1000, k2=3000):
     """Loop iterations/s of a library that can only be driven through solve(): difference of the library's own
     results.time between max_iter=k2 and max_iter=k1 (setup, power iteration and the reference's autotune cancel)."""
@@ -268,6 +323,26 @@ def main():
     pkg = graft.load_package()
     rank, world, local, dist = dist_setup(args.gpus)
     spec = WORKLOADS[args.workload]
+
+    if "batch" in spec:
+        lib = pkg.load_engine() if args.impl == "ours" else (pkg.load_reference() if pkg.REF_LIB_PATH.exists() else None)
+        if args.impl == "reference" and (rank != 0 or lib is None):
+            if rank == 0:
+                print(json.dumps(dict(impl="reference", unavailable="oracle/_ref/libhprlp_ref.so was not built")))
+            return 0
+        if args.impl == "reference":
+            world, dist = 1, None          # the reference is single-GPU: rank 0 runs the whole batch
+        sys.stdout.flush()
+        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
+        try:
+            out = run_batched(args, pkg, spec, lib, rank, world, local, dist, args.impl)
+        finally:
+            os.dup2(saved, 1); os.close(devnull); os.close(saved)
+        if rank == 0:
+            print(json.dumps(out))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     if args.impl == "reference":
         if rank != 0:
