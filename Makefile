@@ -14,7 +14,7 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CUDA_PATH)/include
 LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread
 RPATH := -Xlinker -rpath -Xlinker $(CUDA_PATH)/lib64
 
-CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu
+CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu
 CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp
 OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
 

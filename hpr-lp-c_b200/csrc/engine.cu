@@ -334,7 +334,8 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
     HPR_CUDA_CHECK(cudaMemcpyAsync(A.rowPtr, lp->A->rowPtr, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
     HPR_CUDA_CHECK(cudaMemcpyAsync(A.col, lp->A->colIndex, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
     HPR_CUDA_CHECK(cudaMemcpyAsync(A.val, lp->A->value, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
-    {
+    static const bool host_transpose = getenv("HPRLP_HOST_TRANSPOSE") != nullptr;
+    if (host_transpose) {
         std::vector<int> trp((size_t)n + 1), tci((size_t)nnz);
         std::vector<double> tv((size_t)nnz);
         csr_transpose_host(m, n, (int)nnz, lp->A->rowPtr, lp->A->colIndex, lp->A->value, trp.data(), tci.data(), tv.data());
@@ -342,6 +343,9 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(AT.col, tci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
         HPR_CUDA_CHECK(cudaMemcpyAsync(AT.val, tv.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
         HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    } else {
+        // A^T built on the device in the reference's entry order (stable sort by column), transpose.cu
+        device_transpose_csr(m, n, (int)nnz, A.rowPtr, A.col, A.val, AT.rowPtr, AT.col, AT.val, stream);
     }
     AL = dalloc<double>(m); AU = dalloc<double>(m); c = dalloc<double>(n); l = dalloc<double>(n); u = dalloc<double>(n);
     HPR_CUDA_CHECK(cudaMemcpyAsync(AL, lp->AL, sizeof(double) * m, cudaMemcpyHostToDevice, stream));

@@ -155,6 +155,9 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp);
 void csr_transpose_host(int rows, int cols, int nnz, const int *rp, const int *ci, const double *v,
                         int *trp, int *tci, double *tv);
 
+void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
+                          int *d_trp, int *d_tcol, double *d_tval, cudaStream_t st);
+
 // presolve bridge (presolve.cpp); returns false when unavailable / failed (caller solves the original model)
 bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);
 void presolve_postsolve(HPRLP_results *result, const LP_info_cpu *original, void *handle,
