@@ -11,11 +11,11 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC \
            -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xcompiler -fopenmp -Iinclude
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CUDA_PATH)/include
-LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread
+LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread -ldl
 RPATH := -Xlinker -rpath -Xlinker $(CUDA_PATH)/lib64
 
-CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu
-CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp
+CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu $(SRC)/partitioned.cu
+CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp $(SRC)/nccl_shim.cpp
 OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
 
 all: $(LIB)/libhprlp.so $(LIB)/libhprlp.a $(BUILD)/solve_mps_file

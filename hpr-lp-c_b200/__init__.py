@@ -91,7 +91,7 @@ REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve
 EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
                     "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
                     "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
-                    "hprlp_b200_solve_batched_multi", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
+                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
 
 
 def _dp(a):
@@ -159,6 +159,8 @@ class HprLib:
             L.hprlp_b200_scale_only.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)] + [c_double_p, c_int_p, c_int_p] + \
                 [c_double_p] * 9
             L.hprlp_b200_version.restype = C.c_char_p
+            L.hprlp_b200_solve_partitioned.restype = Results
+            L.hprlp_b200_solve_partitioned.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_int, C.c_int, C.POINTER(B200Info)]
             L.hprlp_b200_solve_batched_multi.restype = BatchedResults
             L.hprlp_b200_solve_batched_multi.argtypes = L.solve_batched.argtypes + [C.c_int]
 
@@ -226,6 +228,14 @@ class HprLib:
         out = self._take(res, m, n)
         out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         out["trace"] = {int(k): (tx[i].copy(), ty[i].copy(), tz[i].copy()) for i, k in enumerate(ti)}
+        return out
+
+    def solve_partitioned(self, model, param, n_gpus, quiet=True):
+        mm = model.contents
+        info = B200Info()
+        res = self.lib.hprlp_b200_solve_partitioned(model, C.byref(param), int(n_gpus), 1 if quiet else 0, C.byref(info))
+        out = self._take(res, mm.m, mm.n)
+        out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         return out
 
     def power_start(self, m, device=0):

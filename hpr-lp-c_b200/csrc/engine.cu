@@ -10,6 +10,7 @@
 #include <curand.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -167,6 +168,59 @@ __global__ void unscale_kernel(const double *x_bar, const double *z_bar, const d
     }
 }
 
+// ---- row-partitioned mode: unfused x-side kernels (the x-side is replicated on every GPU) -------------------
+// x-update from the all-reduced w = A^T y (same arithmetic as XPhaseOp::row)
+template <bool CHECK>
+__global__ void __launch_bounds__(kVecThreads) x_update_kernel(const double *w, double *x, double *x_hat, const double *c, const double *l,
+                                                              const double *u, const double *x0, double *x_bar, double *z_bar,
+                                                              double *x_tmp, const double *params, const int *kx, int *ky, int n) {
+    const double sigma = params[0];
+    const int k = *kx;
+    const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double xi = x[j];
+        const double zt = fma(sigma, w[j] - c[j], xi);
+        const double xb = fmin(u[j], fmax(l[j], zt));
+        const double xh = 2.0 * xb - xi;
+        x[j] = fma(f2, xh, f1 * x0[j]);
+        x_hat[j] = xh;
+        if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
+    }
+}
+// dual residual terms from the all-reduced w = A^T y_bar (same slots as ResidualDualOp)
+template <bool GAP, bool ITER0>
+__global__ void __launch_bounds__(kVecThreads) residual_dual_kernel(const double *w, const double *c, const double *z_bar, const double *x_bar,
+                                                                   const double *x_tmp, const double *col_norm, const double *l,
+                                                                   const double *u, int n, double *partials) {
+    double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double cj = c[j], zb = z_bar[j], xb = x_bar[j], cn = col_norm[j];
+        const double rd = (cj - w[j] - zb) * cn;
+        t[0] += rd * rd; t[1] += cj * xb; t[2] += xb * zb;
+        if (GAP) { const double dx = x_tmp[j]; t[3] += dx * dx; }
+        if (ITER0) {
+            const double lj = l[j], uj = u[j];
+            const double viol = (xb < lj) ? (lj - xb) : ((xb > uj) ? (xb - uj) : 0.0);
+            const double q = viol / cn;
+            t[4] += q * q;
+        }
+    }
+    vec_block_store<5>(t, partials);
+}
+// column statistics after the cross-GPU reduction: sqrt + clamp (Ruiz / Pock-Chambolle), mean (Curtis-Reid)
+__global__ void sqrt_clamp_kernel(double *v, int len) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+        double r = sqrt(v[i]);
+        if (r < 1e-15) r = 1.0;
+        v[i] = r;
+    }
+}
+__global__ void mean_kernel(double *sum, const double *cnt, int len) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x)
+        sum[i] = cnt[i] > 0.0 ? sum[i] / cnt[i] : 0.0;
+}
+
 static inline int vec_grid(int len) {
     int g = (len + kVecThreads - 1) / kVecThreads;
     return std::max(1, std::min(g, kVecBlocks));
@@ -191,12 +245,14 @@ static thread_local long long g_fixup_launches = 0;   // fix-up launches issued 
 template <class Op, int G>
 static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
     constexpr size_t bytes = stream_smem_bytes<Op>();
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static std::atomic<unsigned> configured{0};   // per instantiation, one bit per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured.load() & (1u << dev))) {
         HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (const char *e = getenv("HPRLP_CARVEOUT"))   // tuning hook: shared-memory carve-out in percent
             HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-        configured = true;
+        configured.fetch_or(1u << dev);
     }
     csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
     // rows cut by item boundaries: summed in item order + epilogue (stream order makes the partials visible)
@@ -289,13 +345,12 @@ static int pick_lanes(double mean_len, const char *env_name) {
         const int g = atoi(e);
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
     }
-    // lanes per row ~ mean_len / 6, power of two (measured row-length statistic of this matrix)
-    if (mean_len < 6.0) return 1;
-    if (mean_len < 12.0) return 2;
-    if (mean_len < 24.0) return 4;
-    if (mean_len < 48.0) return 8;
-    if (mean_len < 96.0) return 16;
-    return 32;
+    // Lanes per row from the measured mean row length of this matrix.  Every extra lane costs shuffle
+    // wavefronts on the L1 data stage (the binding unit), so few lanes win: B200 sweep on C2/C3
+    // (gpurun_out_14/15): mean 10 and 20 -> 1 lane best; mean 50 and 100 -> 8 lanes best (4 and 16 within 3 %).
+    if (mean_len < 28.0) return 1;
+    if (mean_len < 40.0) return 4;
+    return 8;
 }
 
 void Engine::finish_matrix(DevCsr &M) {
@@ -374,6 +429,12 @@ Engine::~Engine() {
     if (stream) cudaStreamDestroy(stream);
 }
 
+void Engine::allreduce(double *buf, size_t count, bool max_op) {
+    if (!comm) return;
+    const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, max_op ? kNcclMax : kNcclSum, comm, stream);
+    if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce failed: ") + nccl().GetErrorString(rc));
+}
+
 void Engine::fetch_scalars(int count) {
     HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -393,6 +454,7 @@ void Engine::scale(const HPRLP_parameters *p) {
         norm_bc_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(AL, AU, m, c, n, d_partials);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 2, d_scal);
         launches += 2;
+        allreduce(d_scal, 1);   // |b|^2 is a sum over (partitioned) rows; |c|^2 is replicated
         fetch_scalars(2);
         *nb = sqrt(h_scal[0]);
         *nc = sqrt(h_scal[1]);
@@ -409,10 +471,17 @@ void Engine::scale(const HPRLP_parameters *p) {
         fill_kernel<<<gn, kVecThreads, 0, stream>>>(t2, n, 0.0);
         launches += 2;
         for (int it = 0; it < 20; ++it) {
-            CurtisReidOp oa; oa.other = t2; oa.out = t1;
+            CurtisReidOp<false> oa; oa.other = t2; oa.out = t1; oa.cnt_out = nullptr;
             launch_stream(A, oa, stream);
-            CurtisReidOp ob; ob.other = t1; ob.out = t2;
-            launch_stream(AT, ob, stream);
+            if (!dist()) {
+                CurtisReidOp<false> ob; ob.other = t1; ob.out = t2; ob.cnt_out = nullptr;
+                launch_stream(AT, ob, stream);
+            } else {   // column means over ALL rows: local sums and counts, cross-GPU sum, divide
+                CurtisReidOp<true> ob; ob.other = t1; ob.out = t2; ob.cnt_out = x_tmp;
+                launch_stream(AT, ob, stream);
+                allreduce(t2, n); allreduce(x_tmp, n);
+                mean_kernel<<<gn, kVecThreads, 0, stream>>>(t2, x_tmp, n);
+            }
             launches += 2;
         }
         exp_clamp_kernel<<<gm, kVecThreads, 0, stream>>>(t1, m);
@@ -427,12 +496,17 @@ void Engine::scale(const HPRLP_parameters *p) {
     const int rounds = ruiz_rounds + (p->use_Pock_Chambolle_scaling ? 1 : 0);
     for (int it = 0; it < rounds; ++it) {
         // both statistics are taken from the matrix before either factor is applied (:127-144)
-        if (it < ruiz_rounds) {
-            RowNormOp<true> oa; oa.out = t1; launch_stream(A, oa, stream);
-            RowNormOp<true> ob; ob.out = t2; launch_stream(AT, ob, stream);
-        } else {
-            RowNormOp<false> oa; oa.out = t1; launch_stream(A, oa, stream);
-            RowNormOp<false> ob; ob.out = t2; launch_stream(AT, ob, stream);
+        const bool is_max = it < ruiz_rounds;
+        if (is_max) { RowNormOp<true, false> oa; oa.out = t1; launch_stream(A, oa, stream); }
+        else        { RowNormOp<false, false> oa; oa.out = t1; launch_stream(A, oa, stream); }
+        if (!dist()) {
+            if (is_max) { RowNormOp<true, false> ob; ob.out = t2; launch_stream(AT, ob, stream); }
+            else        { RowNormOp<false, false> ob; ob.out = t2; launch_stream(AT, ob, stream); }
+        } else {       // column statistic over ALL rows: raw local max / sum, cross-GPU reduce, then sqrt + clamp
+            if (is_max) { RowNormOp<true, true> ob; ob.out = t2; launch_stream(AT, ob, stream); }
+            else        { RowNormOp<false, true> ob; ob.out = t2; launch_stream(AT, ob, stream); }
+            allreduce(t2, n, is_max);
+            sqrt_clamp_kernel<<<gn, kVecThreads, 0, stream>>>(t2, n);
         }
         scale_values_kernel<true, true, int><<<A.n_items, kThreads, 0, stream>>>(vA, A.val, t1, t2);
         scale_values_kernel<true, false, int><<<AT.n_items, kThreads, 0, stream>>>(vAT, AT.val, t2, t1);
@@ -468,16 +542,26 @@ void Engine::power_start_vector(double *d_z) {
     // cuRAND XORWOW (CURAND_RNG_PSEUDO_DEFAULT), seed 1, N(0,1), then + 1e-8.  For odd m the reference's
     // unchecked curandGenerateNormalDouble fails with LENGTH_NOT_MULTIPLE and leaves z = 0 (its Ax
     // buffer after the warm-up SpMV with x_bar = 0, src/preprocess.cu:153-156) => z = 1e-8 * ones.
-    HPR_CUDA_CHECK(cudaMemsetAsync(d_z, 0, sizeof(double) * m, stream));
-    if ((m % 2) == 0) {
+    const int mg = dist() ? m_global : m;
+    double *gen_buf = d_z;
+    if (dist()) {   // every GPU draws the global vector (same seed) and keeps its own row block
+        HPR_CUDA_CHECK(cudaMalloc(&gen_buf, sizeof(double) * (size_t)mg));
+    }
+    HPR_CUDA_CHECK(cudaMemsetAsync(gen_buf, 0, sizeof(double) * mg, stream));
+    if ((mg % 2) == 0) {
         curandGenerator_t gen = nullptr;
         if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
             throw std::runtime_error("curandCreateGenerator failed");
         curandSetStream(gen, stream);
         curandSetPseudoRandomGeneratorSeed(gen, 1ULL);
-        curandGenerateNormalDouble(gen, d_z, (size_t)m, 0.0, 1.0);
+        curandGenerateNormalDouble(gen, gen_buf, (size_t)mg, 0.0, 1.0);
         HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
         curandDestroyGenerator(gen);
+    }
+    if (dist()) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(d_z, gen_buf + row0, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        cudaFree(gen_buf);
     }
     add_scalar_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(d_z, m, 1e-8);
     launches++;
@@ -494,20 +578,24 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, m, d_partials);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal);
     launches += 2;
+    allreduce(d_scal, 1);
     double lambda = 1.0;
     int it;
     for (it = 1; it <= max_iter; ++it) {
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
         SpmvOp<false> o1; o1.g = q; o1.out = atq; o1.q = nullptr; o1.partials = nullptr;
         launch_stream(AT, o1, stream);
+        allreduce(atq, n);   // A^T q = sum over row blocks
         SpmvOp<true> o2; o2.g = atq; o2.out = z; o2.q = q; o2.partials = d_partials;
         launch_stream(A, o2, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
+        allreduce(d_scal, 2);
         launches += 4;
         if (it % 10 == 0) {
             power_error_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, q, d_scal + 1, m, d_partials);
             final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
             launches += 2;
+            allreduce(d_scal + 2, 1);
             fetch_scalars(3);
             lambda = h_scal[1];
             if (sqrt(h_scal[2]) < tol) break;
@@ -541,6 +629,28 @@ void Engine::upload_params() {   // reference reset_/upload_halpern_*_params, sr
 void Engine::reset_halpern_counter() { HPR_CUDA_CHECK(cudaMemsetAsync(d_k, 0, 2 * sizeof(int), stream)); }
 
 void Engine::launch_iteration(bool check) {
+    if (dist()) {
+        // Row-partitioned x-phase: partial w_p = A_p^T y_p, NCCL all-reduce over the row blocks (NVLink), then the
+        // replicated x-update; the y-phase stays fused (local rows of A, full x_hat).  SURVEY.md 8e.
+        SpmvOp<false> ow; ow.g = y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+        launch_stream(AT, ow, stream);
+        allreduce(wn, n);
+        if (check) {
+            x_update_kernel<true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, n);
+            YPhaseOp<true> oy;
+            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+            launch_stream_hot(A, oy, stream);
+        } else {
+            x_update_kernel<false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, n);
+            YPhaseOp<false> oy;
+            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+            launch_stream_hot(A, oy, stream);
+        }
+        launches += 3;
+        return;
+    }
     if (check) {
         XPhaseOp<true> ox;
         ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
@@ -570,7 +680,7 @@ void Engine::run_normal(int count) {
     static const bool no_graph = getenv("HPRLP_NO_GRAPH") != nullptr;
     while (count > 0) {
         int len = std::min(count, 128);
-        if (no_graph || len < 2) {
+        if (no_graph || len < 2 || dist()) {
             for (int i = 0; i < len; ++i) launch_iteration(false);
         } else {
             auto it = graphs_.find(len);
@@ -600,10 +710,20 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         o.y_bar = y_bar; o.c = c; o.z_bar = z_bar; o.x_bar = x_bar; o.x_tmp = x_tmp; o.col_norm = col_norm;
         o.l = l; o.u = u; o.partials = d_partials;
     };
+    if (dist()) {
+        SpmvOp<false> ow; ow.g = y_bar; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+        launch_stream(AT, ow, stream);
+        allreduce(wn, n);
+        if (iter == 0) residual_dual_kernel<false, true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
+        else if (compute_gap) residual_dual_kernel<true, false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
+        else residual_dual_kernel<false, false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 5, d_scal);   // x-side sums are replicated: no reduce
+    } else {
     if (iter == 0) { ResidualDualOp<false, true> o; fill_dual(o); launch_stream(AT, o, stream); }
     else if (compute_gap) { ResidualDualOp<true, false> o; fill_dual(o); launch_stream(AT, o, stream); }
     else { ResidualDualOp<false, false> o; fill_dual(o); launch_stream(AT, o, stream); }
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(AT), 5, d_scal);
+    }
     auto fill_primal = [&](auto &o) {
         o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
         o.y_bar = y_bar; o.y_tmp = y_tmp; o.partials = d_partials;
@@ -612,6 +732,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     else { ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream); }
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 4, d_scal + 5);
     launches += 4;
+    allreduce(d_scal + 5, 4);   // y-side sums are partial per row block
     fetch_scalars(9);
     HPR_CUDA_CHECK(cudaGetLastError());
 
@@ -646,6 +767,7 @@ double Engine::weighted_norm_after_restart() {
     WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
     launch_stream(A, o, stream);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
+    allreduce(d_scal, 2);
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp, n, d_partials);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
     launches += 4;
@@ -670,6 +792,7 @@ void Engine::restart_and_sigma(RestartState *rs, const Residuals &res) {
     restart_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_bar, x0, x, n, y_bar, y0, y, m, d_partials);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 2, d_scal);
     launches += 2;
+    allreduce(d_scal + 1, 1);   // |y_bar - y0|^2 is partial per row block, |x_bar - x0|^2 replicated
     fetch_scalars(2);
     const double primal_move = sqrt(h_scal[0]);
     const double dual_move = sqrt(h_scal[1]);
@@ -820,7 +943,15 @@ bool Engine::solve_advance(const HPRLP_parameters *param, SolveHooks *hooks, int
         const bool compute_gap = periodic && iter > 0;
         compute_residuals(iter, compute_gap, &res, &rs);
 
-        const double elapsed = now_seconds() - t_start_alg;
+        double elapsed = now_seconds() - t_start_alg;
+        if (dist()) {   // every rank must take the same TIME_LIMIT decision: use the maximum over ranks
+            h_scal[15] = elapsed;
+            HPR_CUDA_CHECK(cudaMemcpyAsync(d_scal + 15, h_scal + 15, sizeof(double), cudaMemcpyHostToDevice, stream));
+            allreduce(d_scal + 15, 1, true);
+            HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal + 15, d_scal + 15, sizeof(double), cudaMemcpyDeviceToHost, stream));
+            HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+            elapsed = h_scal[15];
+        }
         const char *status = "CONTINUE";   // reference check_stopping, src/main_iterate.cu:406-420
         if (res.kkt < param->stop_tol) status = "OPTIMAL";
         else if (iter >= param->max_iter) status = "ITER_LIMIT";

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/structs.h"
+#include "nccl_shim.h"
 
 namespace hpr {
 
@@ -121,6 +122,12 @@ class Engine {
     int m = 0, n = 0;
     long long nnz = 0;
     int device = 0;
+    // Row-block partition over several GPUs: this engine owns rows [row0, row0+m) of a global
+    // m_global x n problem; x-side vectors are replicated, y-side vectors are local.  comm == nullptr: single GPU.
+    NcclComm comm = nullptr;
+    int nranks = 1, rank = 0, m_global = 0, row0 = 0;
+    bool dist() const { return comm != nullptr; }
+    void allreduce(double *buf, size_t count, bool max_op = false);
     DevCsr A, AT;
     double *AL = nullptr, *AU = nullptr, *c = nullptr, *l = nullptr, *u = nullptr;
     double *row_norm = nullptr, *col_norm = nullptr;

@@ -490,28 +490,34 @@ struct SpmvOp : OpBase {
 };
 
 // Row statistic for Ruiz (sqrt max|a|) and Pock-Chambolle (sqrt sum|a|) scaling
-// (reference CSR_A_row_norm_kernel, HPR_cuda_kernels.cu:91-120); <1e-15 -> 1.
-template <bool MAX>
+// (reference CSR_A_row_norm_kernel, HPR_cuda_kernels.cu:91-120); <1e-15 -> 1.  RAW: store max / sum only (the
+// row-partitioned mode reduces the column statistic across GPUs before the sqrt + clamp).
+template <bool MAX, bool RAW>
 struct RowNormOp : OpBase {
     static constexpr bool kMax = MAX;
     double *out;
     __device__ __forceinline__ void elem(double v, int, double (&o)[1]) const { o[0] = fabs(v); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
+        if (RAW) { out[i] = acc[0]; return; }
         double r = sqrt(acc[0]);
         if (r < 1e-15) r = 1.0;
         out[i] = r;
     }
 };
 
-// Curtis-Reid log-domain sweep (reference curtis_reid_log_update_kernel, src/scaling.cu:5-31).
+// Curtis-Reid log-domain sweep (reference curtis_reid_log_update_kernel, src/scaling.cu:5-31).  RAW: store the
+// sum and the entry count (row-partitioned mode: mean over all GPUs' entries).
+template <bool RAW>
 struct CurtisReidOp : OpBase {
     const double *other;
     double *out;
+    double *cnt_out;
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const {
         o[0] = -log(fmax(fabs(v), 1e-300)) - __ldg(other + col);
     }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long p0, long long p1) const {
         const long long cnt = p1 - p0;
+        if (RAW) { out[i] = acc[0]; cnt_out[i] = (double)cnt; return; }
         out[i] = cnt > 0 ? acc[0] / (double)cnt : 0.0;
     }
 };

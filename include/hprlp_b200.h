@@ -67,6 +67,13 @@ HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, i
                                                      const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
                                                      const HPRLP_parameters *param, int n_gpus);
 
+/* One LP row-block partitioned over n_gpus GPUs of one node (devices param->device_number ...): NCCL all-reduce of
+ * A^T y per iteration over NVLink, fused y-phase on the local rows, all-reduce of <= 4 residual scalars per check.
+ * Same results struct as solve(); no presolve.  n_gpus is clamped to the visible devices; 1 GPU = HPRLP_main_solve.
+ * (new functionality; the reference is single-GPU) */
+HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, const HPRLP_parameters *param, int n_gpus,
+                                           int quiet, hprlp_b200_info *info);
+
 /* cudaProfilerStart/Stop of the library's (statically linked) CUDA runtime: lets `ncu --profile-from-start off`
  * capture only the timed region of bench.py. */
 void hprlp_b200_profiler_start(void);
