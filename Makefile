@@ -14,9 +14,24 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CUDA_PATH)/include
 LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread -ldl
 RPATH := -Xlinker -rpath -Xlinker $(CUDA_PATH)/lib64
 
+# PSLP presolver (third-party, Apache-2.0): compiled from where its sources lie when present, never copied here
+PSLP_DIR ?= /root/reference/third_party/PSLP
+ifneq ($(wildcard $(PSLP_DIR)/src/core/Presolver.c),)
+PSLP_SRCS := $(filter-out $(PSLP_DIR)/src/core/Debugger.c,$(wildcard $(PSLP_DIR)/src/core/*.c)) $(wildcard $(PSLP_DIR)/src/explorers/*.c)
+PSLP_OBJS := $(patsubst $(PSLP_DIR)/src/%.c,$(BUILD)/pslp/%.o,$(PSLP_SRCS))
+PSLP_INC := -I$(PSLP_DIR)/include/PSLP -I$(PSLP_DIR)/include/core -I$(PSLP_DIR)/include/data_structures -I$(PSLP_DIR)/include/explorers
+CXXFLAGS += -DHPRLP_WITH_PSLP $(PSLP_INC)
+else
+# prebuilt objects shipped with the snapshot (the GPU box has no reference tree)
+PSLP_OBJS := $(wildcard $(BUILD)/pslp/core/*.o) $(wildcard $(BUILD)/pslp/explorers/*.o)
+ifneq ($(PSLP_OBJS),)
+$(warning PSLP sources not found; reusing prebuilt objects in $(BUILD)/pslp)
+endif
+endif
+
 CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu $(SRC)/partitioned.cu
 CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp $(SRC)/nccl_shim.cpp
-OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
+OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS)) $(PSLP_OBJS)
 
 all: $(LIB)/libhprlp.so $(LIB)/libhprlp.a $(BUILD)/solve_mps_file
 
@@ -35,6 +50,10 @@ $(LIB)/libhprlp.a: $(OBJS) | $(LIB)
 
 $(BUILD)/solve_mps_file: $(SRC)/solve_mps_file.cpp $(LIB)/libhprlp.a
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -O2 -Iinclude -o $@ $< $(LIB)/libhprlp.a $(LIBS) $(RPATH)
+
+$(BUILD)/pslp/%.o: $(PSLP_DIR)/src/%.c | $(BUILD)
+	@mkdir -p $(dir $@)
+	/usr/bin/gcc -O3 -fPIC $(PSLP_INC) -DPSLP_VERSION=\"0.0.8\" -D_POSIX_C_SOURCE=200809L -DNDEBUG -w -c $< -o $@
 
 $(BUILD) $(LIB):
 	mkdir -p $@

@@ -91,7 +91,7 @@ REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve
 EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
                     "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
                     "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
-                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
+                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
 
 
 def _dp(a):

@@ -342,6 +342,9 @@ T *balloc(size_t count) {
     T *p = nullptr;
     HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
     HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    // cudaMemset runs on the legacy default stream and is asynchronous for device memory; the engine's streams are
+    // non-blocking, so without this barrier a later kernel could be overtaken by the zero-fill.
+    HPR_CUDA_CHECK(cudaDeviceSynchronize());
     return p;
 }
 

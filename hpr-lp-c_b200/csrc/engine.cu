@@ -288,6 +288,9 @@ static T *dalloc(size_t count) {
     T *p = nullptr;
     HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
     HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    // cudaMemset runs on the legacy default stream and is asynchronous for device memory; the engine's streams are
+    // non-blocking, so without this barrier a later kernel could be overtaken by the zero-fill.
+    HPR_CUDA_CHECK(cudaDeviceSynchronize());
     return p;
 }
 static void dfree(void *p) { if (p) cudaFree(p); }
@@ -431,6 +434,8 @@ Engine::~Engine() {
 
 void Engine::allreduce(double *buf, size_t count, bool max_op) {
     if (!comm) return;
+    static const bool skip = getenv("HPRLP_DEBUG_SKIP_ALLREDUCE") != nullptr;   // timing experiments only (wrong results)
+    if (skip) return;
     const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, max_op ? kNcclMax : kNcclSum, comm, stream);
     if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce failed: ") + nccl().GetErrorString(rc));
 }
@@ -679,8 +684,13 @@ void Engine::launch_iteration(bool check) {
 void Engine::run_normal(int count) {
     static const bool no_graph = getenv("HPRLP_NO_GRAPH") != nullptr;
     while (count > 0) {
-        int len = std::min(count, 128);
-        if (no_graph || len < 2 || dist()) {
+        // Graph lengths are restricted to {8, 64} (at most two instantiations per solve: a 64-iteration graph has 256
+        // kernel nodes); the remainder (< 8 iterations) is launched directly.
+        int len = count >= 64 ? 64 : (count >= 8 ? 8 : count);
+        // Graphs only pay when the loop is launch-bound (small matrices) and long enough to amortise the instantiation
+        // (~30 ms for 256 nodes): matrices with >= 2e6 nonzeros keep the host ahead of the GPU with direct launches.
+        const bool want_graph = nnz < 2000000 && loop.iter >= 300;
+        if (no_graph || len < 8 || dist() || !want_graph) {
             for (int i = 0; i < len; ++i) launch_iteration(false);
         } else {
             auto it = graphs_.find(len);

@@ -116,3 +116,43 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, 
     }
     return out;
 }
+
+// Diagnostic: average time (ms) of one ncclAllReduce of `count` doubles issued from one host thread per GPU,
+// exactly as the partitioned solver issues it (tools/partition_study.py reports it next to the solver numbers).
+extern "C" double hprlp_b200_nccl_allreduce_ms(int n_gpus, long long count, int reps) {
+    int avail = 0;
+    cudaGetDeviceCount(&avail);
+    const int P = std::max(1, std::min(n_gpus, avail));
+    if (P < 2) return 0.0;
+    std::vector<int> devs(P);
+    for (int p = 0; p < P; ++p) devs[p] = p;
+    std::vector<NcclComm> comms(P, nullptr);
+    if (nccl().CommInitAll(comms.data(), P, devs.data()) != 0) return -1.0;
+    std::vector<double> ms(P, 0.0);
+    std::vector<std::thread> workers;
+    for (int p = 0; p < P; ++p) {
+        workers.emplace_back([&, p]() {
+            cudaSetDevice(devs[p]);
+            cudaStream_t st;
+            cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            double *buf = nullptr;
+            cudaMalloc(&buf, sizeof(double) * (size_t)count);
+            cudaMemset(buf, 0, sizeof(double) * (size_t)count);
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            for (int i = 0; i < 5; ++i) nccl().AllReduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, comms[p], st);
+            cudaStreamSynchronize(st);
+            cudaEventRecord(e0, st);
+            for (int i = 0; i < reps; ++i) nccl().AllReduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, comms[p], st);
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e0, e1);
+            ms[p] = t / reps;
+            cudaFree(buf); cudaStreamDestroy(st); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int p = 0; p < P; ++p) nccl().CommDestroy(comms[p]);
+    return *std::max_element(ms.begin(), ms.end());
+}

@@ -74,6 +74,12 @@ HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, i
 HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, const HPRLP_parameters *param, int n_gpus,
                                            int quiet, hprlp_b200_info *info);
 
+/* Presolve step only (PSLP bridge, host): fills *reduced and *handle, returns 1 on success, 0 when presolve is
+ * unavailable or failed (the caller then solves the original model, reference src/HPRLP.cu:508-511).
+ * hprlp_b200_presolve_free releases both. */
+int hprlp_b200_presolve(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);
+void hprlp_b200_presolve_free(void *handle, LP_info_cpu *reduced);
+
 /* cudaProfilerStart/Stop of the library's (statically linked) CUDA runtime: lets `ncu --profile-from-start off`
  * capture only the timed region of bench.py. */
 void hprlp_b200_profiler_start(void);

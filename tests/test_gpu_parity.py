@@ -206,3 +206,24 @@ def test_iterates_match_reference_build(pkg, engine, reference, name, backend_cu
         assert a["status"] == b["status"] == "ITER_LIMIT" and a["iter"] == b["iter"] == k
         for nm in "xyz":
             assert rel(a[nm], b[nm]) <= ITER_TOL, (name, k, nm, rel(a[nm], b[nm]))
+
+
+def test_solve_with_presolve_matches_reference(pkg, engine, reference):
+    """Default parameters (use_presolve=true): PSLP reduces the model on the host, the engine solves the reduced LP, the
+    solution is postsolved to the original space -- same status / iterations / objective as the reference build."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent))
+    from test_model_layer import _presolve_lp
+    lp = _presolve_lp(pkg, 1)
+    p = pkg.Parameters.default(stop_tol=1e-6)
+    outs = {}
+    for tag, lib in (("new", engine), ("ref", reference)):
+        model = lib.create_model(lp)
+        outs[tag] = lib.solve(model, p)
+        lib.free_model(model)
+    a, b = outs["new"], outs["ref"]
+    assert a["status"] == b["status"] == "OPTIMAL" and a["iter"] == b["iter"]
+    assert abs(a["primal_obj"] - b["primal_obj"]) <= 1e-9 * (1 + abs(b["primal_obj"]))
+    assert a["x"].shape == (lp["n"],) and a["y"].shape == (lp["m"],)
+    for k in "xyz":
+        assert np.max(np.abs(a[k] - b[k])) <= 1e-8 * max(1.0, np.max(np.abs(b[k]))), k

@@ -124,3 +124,61 @@ def test_transpose_order_matches_reference_counting_sort(oracle):
     trp, tci, tv = oracle.transpose(50, 30, A.indptr, A.indices, A.data)
     AT = A.T.tocsr(); AT.sort_indices()
     assert np.array_equal(trp, AT.indptr) and np.array_equal(tci, AT.indices) and np.array_equal(tv, AT.data)
+
+
+# ------------------------------------------------------------------------------------------------
+# PSLP presolve hand-off (host): the reduced problem must be bit-identical to the reference's
+# ("presolve output ... bit-exact"); the reference runs PSLP in a forked worker, we run it in-process.
+# ------------------------------------------------------------------------------------------------
+def _presolve_lp(pkg, seed):
+    """LP with presolve opportunities: singleton rows/columns, duplicate rows, fixed variables, empty column."""
+    rng = np.random.default_rng(seed)
+    base = pkg.synth_lp("uniform", 60, 140, 60 * 6, seed=pkg.SEED + seed)
+    A = sp.csr_matrix((base["values"], base["colIndex"], base["rowPtr"]), shape=(60, 140)).tolil()
+    A[3, :] = 0; A[3, 7] = 2.0                      # singleton row
+    A[10, :] = A[11, :] * 2.0                      # parallel rows
+    A[:, 20] = 0                                   # empty column
+    A[:, 21] = 0; A[5, 21] = 1.5                   # singleton column
+    A = A.tocsr(); A.sort_indices(); A.eliminate_zeros()
+    lp = dict(m=60, n=140, rowPtr=A.indptr.astype(np.int32), colIndex=A.indices.astype(np.int32), values=A.data.copy())
+    v = pkg.synth_vectors(lp, pkg.SEED + seed, pkg.SEED + seed)      # bounds/cost rebuilt from a feasible primal-dual pair
+    lp.update({k: v[k] for k in ("AL", "AU", "l", "u", "c")})
+    lp["l"][30] = lp["u"][30] = v["xs"][30]         # fixed variable
+    del rng
+    return lp
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_presolve_reduced_model_bit_exact_vs_reference(pkg, engine, reference, seed):
+    import ctypes as C
+    lp = _presolve_lp(pkg, seed) if seed else pkg.TOY_LP
+    p = pkg.Parameters.default()
+    outs = {}
+    # ours: C hook around the in-process PSLP bridge
+    model = engine.create_model(lp)
+    red, h = pkg.LPInfoCpu(), C.c_void_p()
+    engine.lib.hprlp_b200_presolve.argtypes = [C.POINTER(pkg.LPInfoCpu), C.POINTER(pkg.Parameters), C.POINTER(pkg.LPInfoCpu), C.POINTER(C.c_void_p)]
+    ok = engine.lib.hprlp_b200_presolve(model, C.byref(p), C.byref(red), C.byref(h))
+    if not ok:
+        engine.free_model(model)
+        pytest.skip("PSLP not linked into this build of libhprlp.so")
+    outs["new"] = engine.model_arrays(C.pointer(red))
+    engine.lib.hprlp_b200_presolve_free.argtypes = [C.c_void_p, C.POINTER(pkg.LPInfoCpu)]
+    engine.lib.hprlp_b200_presolve_free(h, C.byref(red))
+    engine.free_model(model)
+    # reference: its exported C++ bridge (forked PSLP worker), src/pslp_integration.cpp:628
+    f = getattr(reference.lib, "_Z26run_embedded_pslp_presolvePK11LP_info_cpuPK16HPRLP_parametersPS_PPv")
+    f.restype = C.c_bool
+    f.argtypes = [C.POINTER(pkg.LPInfoCpu), C.POINTER(pkg.Parameters), C.POINTER(pkg.LPInfoCpu), C.POINTER(C.c_void_p)]
+    model = reference.create_model(lp)
+    red2, h2 = pkg.LPInfoCpu(), C.c_void_p()
+    assert f(model, C.byref(p), C.byref(red2), C.byref(h2))
+    outs["ref"] = reference.model_arrays(C.pointer(red2))
+    g = getattr(reference.lib, "_Z28free_embedded_pslp_presolverPv")
+    g.argtypes = [C.c_void_p]
+    g(h2)
+    reference.free_model(model)
+    a, b = outs["new"], outs["ref"]
+    assert (a["m"], a["n"], a["nnz"]) == (b["m"], b["n"], b["nnz"])
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
