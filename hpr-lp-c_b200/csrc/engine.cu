@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#define HPR_SET_TEX(op, t) op.tex = t;
+
 namespace hpr {
 
 // ------------------------------------------------------------------------------------------------
@@ -283,11 +285,24 @@ static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
     else               launch_one<Op, 16>(v, op, st);
 }
 
+// One device arena per engine: a single cudaMalloc + one zero-fill instead of ~45 cudaMalloc/cudaMemset/cudaFree
+// pairs (cudaMalloc/cudaFree of multi-GB buffers are synchronous and cost tens of ms each on the e2e path).
+struct Arena { char *base = nullptr; size_t size = 0, off = 0; };
+static thread_local Arena *g_arena = nullptr;   // set while an engine carves its buffers
+static size_t arena_round(size_t bytes) { return (bytes + 511) / 512 * 512; }   // 512 B: texture base alignment
+
 template <typename T>
 static T *dalloc(size_t count) {
+    const size_t bytes = arena_round(std::max<size_t>(count, 1) * sizeof(T));
+    if (g_arena) {
+        if (g_arena->off + bytes > g_arena->size) throw std::runtime_error("device arena exhausted");
+        T *p = reinterpret_cast<T *>(g_arena->base + g_arena->off);   // arena memory is already zero
+        g_arena->off += bytes;
+        return p;
+    }
     T *p = nullptr;
-    HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    HPR_CUDA_CHECK(cudaMalloc(&p, bytes));
+    HPR_CUDA_CHECK(cudaMemset(p, 0, bytes));
     // cudaMemset runs on the legacy default stream and is asynchronous for device memory; the engine's streams are
     // non-blocking, so without this barrier a later kernel could be overtaken by the zero-fill.
     HPR_CUDA_CHECK(cudaDeviceSynchronize());
@@ -377,6 +392,16 @@ void Engine::alloc_common() {
     d_scal = dalloc<double>(16);
     HPR_CUDA_CHECK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
     HPR_CUDA_CHECK(cudaMallocHost(&h_params, 4 * sizeof(double)));
+    auto make_tex = [](double *ptr, size_t count) {
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ptr;
+        rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = count * sizeof(double);
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t t = 0;
+        HPR_CUDA_CHECK(cudaCreateTextureObject(&t, &rd, &td, nullptr));
+        return t;
+    };
+    tex_y = make_tex(y, m); tex_xhat = make_tex(x_hat, n);
+    tex_q = make_tex(wm2, m); tex_atq = make_tex(wn, n);   // power iteration: q and A^T q
     A.G = pick_lanes(A.mean_len, "HPRLP_LANES_A");
     AT.G = pick_lanes(AT.mean_len, "HPRLP_LANES_AT");
 }
@@ -387,6 +412,35 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
     HPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     m = lp->m; n = lp->n; nnz = lp->A->numElements;
     obj_constant = lp->obj_constant;
+    {
+        // arena size: two padded CSR copies + item tables + 5 problem vectors + 9 n-vectors + 8 m-vectors + partials
+        const size_t ctas = (size_t)((nnz + kChunk - 1) / kChunk) + 1, padded = ctas * kChunk, witems = ctas * kWarps;
+        size_t need = 0;
+        for (size_t rows : {(size_t)m, (size_t)n})
+            need += arena_round((rows + 1) * 4) + arena_round(padded * 4) + arena_round(padded * 8) + arena_round((witems + 1) * 4) +
+                    2 * arena_round(witems * 16) + arena_round(witems * 4);
+        need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((size_t)n * 8);
+        need += arena_round((size_t)(ctas + witems / kWarps + kVecBlocks + 64) * kMaxSlots * 8) + (1u << 16);
+        Arena *ar = new Arena;
+        ar->size = need;
+        // Stream-ordered allocation from the device's default memory pool with an unlimited release threshold: the
+        // arena of a finished solve stays cached in the pool, so repeated solve() calls pay neither cudaMalloc nor
+        // cudaFree (both synchronous and ~0.1-0.5 s for multi-GB buffers).  HPRLP_NO_POOL=1 restores cudaMalloc/cudaFree.
+        static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
+        pooled_ = !no_pool;
+        if (pooled_) {
+            cudaMemPool_t pool = nullptr;
+            HPR_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+            unsigned long long keep = ~0ULL;
+            HPR_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&ar->base), need, stream));
+        } else {
+            HPR_CUDA_CHECK(cudaMalloc(&ar->base, need));
+        }
+        HPR_CUDA_CHECK(cudaMemsetAsync(ar->base, 0, need, stream));
+        arena_ = ar;
+        g_arena = ar;
+    }
     alloc_matrix(A, m, n, nnz);
     alloc_matrix(AT, n, m, nnz);
     HPR_CUDA_CHECK(cudaMemcpyAsync(A.rowPtr, lp->A->rowPtr, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
@@ -414,6 +468,8 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
     finish_matrix(A);
     finish_matrix(AT);
     alloc_common();
+    zo_buf = dalloc<double>(n);
+    g_arena = nullptr;
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
@@ -421,12 +477,14 @@ Engine::~Engine() {
     if (stream) cudaStreamSynchronize(stream);
     for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
     graphs_.clear();
-    free_matrix(A); free_matrix(AT);
-    dfree(AL); dfree(AU); dfree(c); dfree(l); dfree(u);
-    dfree(row_norm); dfree(col_norm);
-    dfree(x); dfree(x0); dfree(x_hat); dfree(x_bar); dfree(z_bar); dfree(x_tmp); dfree(wn);
-    dfree(y); dfree(y0); dfree(y_bar); dfree(y_obj); dfree(y_tmp); dfree(wm); dfree(wm2);
-    dfree(d_params); dfree(d_k); dfree(d_partials); dfree(d_scal);
+    for (cudaTextureObject_t t : {tex_y, tex_xhat, tex_q, tex_atq})
+        if (t) cudaDestroyTextureObject(t);
+    if (arena_) {   // every device buffer of this engine lives in the arena
+        Arena *ar = static_cast<Arena *>(arena_);
+        if (pooled_ && stream) { cudaFreeAsync(ar->base, stream); cudaStreamSynchronize(stream); }
+        else cudaFree(ar->base);
+        delete ar;
+    }
     if (h_scal) cudaFreeHost(h_scal);
     if (h_params) cudaFreeHost(h_params);
     if (stream) cudaStreamDestroy(stream);
@@ -588,11 +646,11 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     int it;
     for (it = 1; it <= max_iter; ++it) {
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
-        SpmvOp<false> o1; o1.g = q; o1.out = atq; o1.q = nullptr; o1.partials = nullptr;
-        launch_stream(AT, o1, stream);
+        SpmvOp<false, true> o1; o1.g = q; o1.tex = tex_q; o1.out = atq; o1.q = nullptr; o1.partials = nullptr;
+        launch_stream_hot(AT, o1, stream);
         allreduce(atq, n);   // A^T q = sum over row blocks
-        SpmvOp<true> o2; o2.g = atq; o2.out = z; o2.q = q; o2.partials = d_partials;
-        launch_stream(A, o2, stream);
+        SpmvOp<true, true> o2; o2.g = atq; o2.tex = tex_atq; o2.out = z; o2.q = q; o2.partials = d_partials;
+        launch_stream_hot(A, o2, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
         allreduce(d_scal, 2);
         launches += 4;
@@ -637,19 +695,19 @@ void Engine::launch_iteration(bool check) {
     if (dist()) {
         // Row-partitioned x-phase: partial w_p = A_p^T y_p, NCCL all-reduce over the row blocks (NVLink), then the
         // replicated x-update; the y-phase stays fused (local rows of A, full x_hat).  SURVEY.md 8e.
-        SpmvOp<false> ow; ow.g = y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+        SpmvOp<false> ow; ow.g = y; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
         launch_stream(AT, ow, stream);
         allreduce(wn, n);
         if (check) {
             x_update_kernel<true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, n);
             YPhaseOp<true> oy;
-            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         } else {
             x_update_kernel<false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, n);
             YPhaseOp<false> oy;
-            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         }
@@ -658,20 +716,20 @@ void Engine::launch_iteration(bool check) {
     }
     if (check) {
         XPhaseOp<true> ox;
-        ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+        ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
         ox.x_bar = x_bar; ox.z_bar = z_bar; ox.x_tmp = x_tmp; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
         launch_stream_hot(AT, ox, stream);
         YPhaseOp<true> oy;
-        oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+        oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
         oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
         launch_stream_hot(A, oy, stream);
     } else {
         XPhaseOp<false> ox;
-        ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+        ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
         ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
         launch_stream_hot(AT, ox, stream);
         YPhaseOp<false> oy;
-        oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+        oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
         oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
         launch_stream_hot(A, oy, stream);
     }
@@ -721,7 +779,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         o.l = l; o.u = u; o.partials = d_partials;
     };
     if (dist()) {
-        SpmvOp<false> ow; ow.g = y_bar; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+        SpmvOp<false> ow; ow.g = y_bar; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
         launch_stream(AT, ow, stream);
         allreduce(wn, n);
         if (iter == 0) residual_dual_kernel<false, true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
@@ -836,7 +894,7 @@ void Engine::restart_and_sigma(RestartState *rs, const Residuals &res) {
 void Engine::collect_solution(double *hx, double *hy, double *hz) {
     // unscale into scratch (wn, x_hat reused as z scratch is NOT allowed: x_hat is live) -> use wn/wm + x_tmp copy
     double *xo = wn, *yo = wm;
-    double *zo = dalloc<double>(n);
+    double *zo = zo_buf;
     unscale_kernel<<<vec_grid(std::max(m, n)), kVecThreads, 0, stream>>>(x_bar, z_bar, col_norm, xo, zo, n, y_bar, row_norm, yo, m,
                                                                          b_scale, c_scale);
     launches++;
@@ -844,7 +902,6 @@ void Engine::collect_solution(double *hx, double *hy, double *hz) {
     HPR_CUDA_CHECK(cudaMemcpyAsync(hy, yo, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
     HPR_CUDA_CHECK(cudaMemcpyAsync(hz, zo, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
-    dfree(zo);
 }
 
 double Engine::time_phase_ms(int which, int reps) {
@@ -854,12 +911,12 @@ double Engine::time_phase_ms(int which, int reps) {
     auto one = [&]() {
         if (which == 0) {
             XPhaseOp<false> ox;
-            ox.y = y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+            ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
             ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
             launch_stream_hot(AT, ox, stream);
         } else {
             YPhaseOp<false> oy;
-            oy.x_hat = x_hat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         }

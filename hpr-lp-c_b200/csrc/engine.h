@@ -148,6 +148,10 @@ class Engine {
     double *h_params = nullptr;     // pinned [4]
     cudaStream_t stream = nullptr;
     long long launches = 0;
+    bool pooled_ = false;
+    void *arena_ = nullptr;         // single device allocation all buffers are carved from
+    double *zo_buf = nullptr;       // n doubles for the unscaled z on output
+    cudaTextureObject_t tex_y = 0, tex_xhat = 0, tex_q = 0, tex_atq = 0;   // gathered vectors bound as int2 linear textures
 
    private:
     void alloc_common();

@@ -43,6 +43,9 @@ constexpr int kWarps = kThreads / 32;
 #ifndef HPR_MIN_BLOCKS
 #define HPR_MIN_BLOCKS 8
 #endif
+#ifndef HPR_TEX_GATHER
+#define HPR_TEX_GATHER 1
+#endif
 constexpr int kLaneNnz = HPR_LANE_NNZ;          // nonzeros per lane per item
 constexpr int kRoundNnz = HPR_ROUND_NNZ;        // nonzeros per lane per load round (loads in flight)
 constexpr int kWarpChunk = 32 * kLaneNnz;       // nonzeros per warp item
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
             for (int u = 0; u < kRoundNnz / 2; ++u) {
                 double o0[NV], o1[NV];
                 op.elem(vv[u].x, cc[u].x, o0);
-                op.elem(vv[u].y, cc[u].y, o1);
+                op.elem_b(vv[u].y, cc[u].y, o1);
                 const int t = (rd * (kRoundNnz / 2) + u) * 32 + lane;
 #pragma unroll
                 for (int q = 0; q < NV; ++q)
@@ -343,7 +346,16 @@ struct XPhaseOp : OpBase {
         f2 = 1.0 - f1;
         if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
     }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(y + col); }
+    // Gathers are split between the two L1 pipes: HPR_TEX_GATHER == 0 all through the LSU (ld.global.nc),
+    // 1 all through the TEX pipe (y bound as an int2 linear texture), 2 first nonzero of each pair LSU, second TEX.
+    cudaTextureObject_t tex;
+    __device__ __forceinline__ double g_lsu(int col) const { return __ldg(y + col); }
+    __device__ __forceinline__ double g_tex(int col) const {
+        const int2 t = tex1Dfetch<int2>(tex, col);
+        return __hiloint2double(t.y, t.x);
+    }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER == 1 ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER >= 1 ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const {
         const double xi = x[j];
         const double zt = fma(sigma, acc[0] - c[j], xi);
@@ -381,7 +393,14 @@ struct YPhaseOp : OpBase {
         f2 = 1.0 - f1;
         if (blockIdx.x == 0 && threadIdx.x == 0) *kx = k + 1;
     }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(x_hat + col); }
+    cudaTextureObject_t tex;   // x_hat as an int2 linear texture (see XPhaseOp)
+    __device__ __forceinline__ double g_lsu(int col) const { return __ldg(x_hat + col); }
+    __device__ __forceinline__ double g_tex(int col) const {
+        const int2 t = tex1Dfetch<int2>(tex, col);
+        return __hiloint2double(t.y, t.x);
+    }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER == 1 ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER >= 1 ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
         const double yi = y[i];
         const double v = fma(-lamsig, yi, acc[0]);
@@ -410,6 +429,7 @@ struct ResidualDualOp : OpBase {
         for (int s = 0; s < 5; ++s) t[s] = 0.0;
     }
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(y_bar + col); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) {
         const double cj = c[j], zb = z_bar[j], xb = x_bar[j], cn = col_norm[j];
         const double rd = (cj - acc[0] - zb) * cn;
@@ -443,6 +463,7 @@ struct ResidualPrimalOp : OpBase {
         o[0] = v * __ldg(x_bar + col);
         if (GAP) o[NV - 1] = v * __ldg(x_tmp + col);
     }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[NV]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[NV], long long, long long) {
         const double ax = acc[0];
         const double rp = fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax) * row_norm[i];
@@ -461,6 +482,7 @@ struct WeightedNormOp : OpBase {
     double t[2];
     __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(dx + col); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) {
         const double d = dy[i];
         t[0] += acc[0] * d;
@@ -471,15 +493,24 @@ struct WeightedNormOp : OpBase {
 
 // Plain SpMV out = M * g, with optional fused <out,out> and <q,out> (power iteration,
 // reference src/power_iteration.cu:73-90).
-template <bool DOTS>
+template <bool DOTS, bool TEX = false>
 struct SpmvOp : OpBase {
     const double *g;
+    cudaTextureObject_t tex;   // g as an int2 linear texture when TEX (gathers through the TEX pipe, see XPhaseOp)
     double *out;
     const double *q;
     double *partials;
     double t[2];
     __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(g + col); }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const {
+        if (TEX) {
+            const int2 w = tex1Dfetch<int2>(tex, col);
+            o[0] = v * __hiloint2double(w.y, w.x);
+        } else {
+            o[0] = v * __ldg(g + col);
+        }
+    }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) {
         out[i] = acc[0];
         if (DOTS) { t[0] += acc[0] * acc[0]; t[1] += q[i] * acc[0]; }
@@ -497,6 +528,7 @@ struct RowNormOp : OpBase {
     static constexpr bool kMax = MAX;
     double *out;
     __device__ __forceinline__ void elem(double v, int, double (&o)[1]) const { o[0] = fabs(v); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
         if (RAW) { out[i] = acc[0]; return; }
         double r = sqrt(acc[0]);
@@ -515,6 +547,7 @@ struct CurtisReidOp : OpBase {
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const {
         o[0] = -log(fmax(fabs(v), 1e-300)) - __ldg(other + col);
     }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long p0, long long p1) const {
         const long long cnt = p1 - p0;
         if (RAW) { out[i] = acc[0]; cnt_out[i] = (double)cnt; return; }
