@@ -232,13 +232,14 @@ static inline int vec_grid(int len) {
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 // per-CTA partial blocks written by one streamed pass: main-kernel CTAs + fix-up CTAs
-static int part_blocks(const DevCsr &M) { return M.n_items + (M.n_items * kWarps + kThreads - 1) / kThreads; }
+static int part_blocks(const DevCsr &M) { return M.n_items + (M.n_cut + kThreads - 1) / kThreads; }
 
 static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
     v.head_part = M.head_part; v.tail_part = M.tail_part; v.counters = M.counters;
+    v.n_cut = M.n_cut; v.cut_row = M.cut_row; v.cut_ia = M.cut_ia; v.cut_ib = M.cut_ib;
     return v;
 }
 
@@ -258,10 +259,10 @@ static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
     }
     csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
     // rows cut by item boundaries: summed in item order + epilogue (stream order makes the partials visible)
-    const int n_real = (int)((v.nnz + kWarpChunk - 1) / kWarpChunk);
-    const int n_fix = (v.n_items * kWarps + kThreads - 1) / kThreads;
-    csr_fixup_kernel<Op, int><<<n_fix, kThreads, 0, st>>>(v, op, n_real, v.n_items);
-    g_fixup_launches++;
+    if (v.n_cut > 0) {
+        csr_fixup_kernel<Op, int><<<(v.n_cut + kThreads - 1) / kThreads, kThreads, 0, st>>>(v, op, v.n_items);
+        g_fixup_launches++;
+    }
 }
 
 template <class Op>
@@ -351,6 +352,7 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.head_part = dalloc<double>(witems * 2);
     M.tail_part = dalloc<double>(witems * 2);
     M.counters = dalloc<unsigned>(witems);
+    M.cut_row = dalloc<int>(witems); M.cut_ia = dalloc<int>(witems); M.cut_ib = dalloc<int>(witems);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
@@ -377,6 +379,10 @@ void Engine::finish_matrix(DevCsr &M) {
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
+    // compact list of the rows cut by item boundaries (item order): flags -> exclusive scan -> scatter
+    const int n_real = (int)((M.nnz + kWarpChunk - 1) / kWarpChunk);
+    M.n_cut = build_cut_list(M.rowPtr, M.item_row, M.rows, n_real, M.cut_row, M.cut_ia, M.cut_ib, stream);
+    launches += 3;
 }
 
 void Engine::alloc_common() {
@@ -418,7 +424,7 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
         size_t need = 0;
         for (size_t rows : {(size_t)m, (size_t)n})
             need += arena_round((rows + 1) * 4) + arena_round(padded * 4) + arena_round(padded * 8) + arena_round((witems + 1) * 4) +
-                    2 * arena_round(witems * 16) + arena_round(witems * 4);
+                    2 * arena_round(witems * 16) + 4 * arena_round(witems * 4);
         need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((size_t)n * 8);
         need += arena_round((size_t)(ctas + witems / kWarps + kVecBlocks + 64) * kMaxSlots * 8) + (1u << 16);
         Arena *ar = new Arena;

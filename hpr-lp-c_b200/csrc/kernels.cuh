@@ -64,7 +64,10 @@ struct CsrView {
     int n_items;          // CTAs in the grid
     double *head_part;    // [items * 2] partial of the row entering the item from the left
     double *tail_part;    // [items * 2] partial of the row leaving the item to the right
-    unsigned *counters;   // [items] arrivals per split row (indexed by the item where the row ends)
+    unsigned *counters;   // unused since r1 v2 (kept for layout stability)
+    // rows cut by item boundaries, in item order (built once at setup): row, first and last item it spans
+    int n_cut;
+    const int *cut_row, *cut_ia, *cut_ib;
 };
 
 __device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
@@ -252,55 +255,51 @@ __global__ void build_item_rows_kernel(const RP *rowPtr, int rows, long long nnz
 }
 
 
-// Finalises the rows cut by item boundaries: candidate i = warp item i whose first row entered from the left and
-// ends inside it.  total = tail[ia] + head[ia+1] + ... + head[i] (item order); rows with more than kSeqPartials
-// partials are summed by the whole warp (stride-32 order + xor tree).  One candidate per lane, so the epilogue
-// loads of neighbouring cut rows are issued together.  Partial-sum blocks of reducing ops go to
-// partials[(block_offset + blockIdx.x)].
+// Finalises the rows cut by item boundaries, one cut row per lane from the compact list built at setup
+// (cut_row/cut_ia/cut_ib, item order): total = tail[ia] + head[ia+1] + ... + head[ib]; rows with more than
+// kSeqPartials partials are summed by the whole warp (stride-32 order + xor tree).  The list, the partials, the row
+// pointers and the epilogue inputs are independent loads: two memory latencies instead of the four of a
+// item_row -> rowPtr -> partial -> vector chain.  Partial-sum blocks of reducing ops go to
+// partials[(block_offset + blockIdx.x)].  Not launched at all when the matrix has no cut rows.
 template <class Op, typename RP>
-__global__ void __launch_bounds__(kThreads) csr_fixup_kernel(CsrView<RP> M, Op op, int n_real_items, int block_offset) {
+__global__ void __launch_bounds__(kThreads) csr_fixup_kernel(CsrView<RP> M, Op op, int block_offset) {
     constexpr int NV = Op::NV;
     constexpr bool MX = Op::kMax;
     __shared__ double red_scratch[kMaxSlots * kWarps];
     const int lane = threadIdx.x & 31;
     op.init();
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    int coop = 0, ia = 0, r = 0;
+    const int k = blockIdx.x * kThreads + threadIdx.x;
+    int coop = 0, ia = 0, ib = 0, r = 0;
     long long p0 = 0, p1 = 0;
-    if (i > 0 && i < n_real_items) {
-        r = __ldg(M.item_row + i);
-        const int rnext = __ldg(M.item_row + i + 1);
-        if (r < M.rows && rnext > r) {                       // row r is finalised by item i
-            p0 = (long long)M.rowPtr[r];
-            p1 = (long long)M.rowPtr[r + 1];
-            const long long s = (long long)i * kWarpChunk;
-            if (p0 < s) {                                     // ... and it entered from the left: a cut row
-                ia = (int)(p0 / kWarpChunk);
-                if (i - ia < kSeqPartials) {
-                    double sum[NV];
+    if (k < M.n_cut) {
+        r = __ldg(M.cut_row + k);
+        ia = __ldg(M.cut_ia + k);
+        ib = __ldg(M.cut_ib + k);
+        p0 = (long long)M.rowPtr[r];
+        p1 = (long long)M.rowPtr[r + 1];
+        if (ib - ia < kSeqPartials) {
+            double sum[NV];
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) sum[q] = M.tail_part[(size_t)ia * 2 + q];
-                    for (int k = ia + 1; k <= i; ++k) {
+            for (int q = 0; q < NV; ++q) sum[q] = M.tail_part[(size_t)ia * 2 + q];
+            for (int j = ia + 1; j <= ib; ++j) {
 #pragma unroll
-                        for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], M.head_part[(size_t)k * 2 + q]);
-                    }
-                    op.row(r, sum, p0, p1);
-                } else {
-                    coop = 1;
-                }
+                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], M.head_part[(size_t)j * 2 + q]);
             }
+            op.row(r, sum, p0, p1);
+        } else {
+            coop = 1;
         }
     }
     unsigned pend = __ballot_sync(0xffffffffu, coop);
     while (pend) {
         const int src = __ffs(pend) - 1;
         const int a = __shfl_sync(0xffffffffu, ia, src);
-        const int b = __shfl_sync(0xffffffffu, i, src);
+        const int b = __shfl_sync(0xffffffffu, ib, src);
         double sum[NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q) sum[q] = 0.0;
-        for (int k = a + lane; k <= b; k += 32) {
-            const double *srcp = ((k == a) ? M.tail_part : M.head_part) + (size_t)k * 2;
+        for (int j = a + lane; j <= b; j += 32) {
+            const double *srcp = ((j == a) ? M.tail_part : M.head_part) + (size_t)j * 2;
 #pragma unroll
             for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], srcp[q]);
         }
@@ -313,6 +312,30 @@ __global__ void __launch_bounds__(kThreads) csr_fixup_kernel(CsrView<RP> M, Op o
         pend &= pend - 1;
     }
     op.finish(red_scratch, block_offset + blockIdx.x);
+}
+
+// Setup: flag[i] = 1 when warp item i finalises a cut row (its first row entered from the left and ends inside it);
+// after an exclusive scan of the flags, scatter (row, first item, last item) into the compact list in item order.
+template <typename RP>
+__global__ void cut_flags_kernel(const RP *rowPtr, const int *item_row, int rows, int n_real_items, int *flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_real_items) return;
+    int f = 0;
+    if (i > 0) {
+        const int r = item_row[i];
+        if (r < rows && item_row[i + 1] > r && (long long)rowPtr[r] < (long long)i * kWarpChunk) f = 1;
+    }
+    flag[i] = f;
+}
+template <typename RP>
+__global__ void cut_scatter_kernel(const RP *rowPtr, const int *item_row, const int *flag, const int *pos, int n_real_items,
+                                   int *cut_row, int *cut_ia, int *cut_ib) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_real_items || !flag[i]) return;
+    const int r = item_row[i];
+    cut_row[pos[i]] = r;
+    cut_ia[pos[i]] = (int)((long long)rowPtr[r] / kWarpChunk);
+    cut_ib[pos[i]] = i;
 }
 
 // ================================================================================================
