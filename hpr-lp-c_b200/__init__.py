@@ -91,7 +91,7 @@ REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve
 EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
                     "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
                     "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
-                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
+                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_solve_partitioned_synth", "hprlp_b200_synth_rows", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
 
 
 def _dp(a):
@@ -159,6 +159,11 @@ class HprLib:
             L.hprlp_b200_scale_only.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters)] + [c_double_p, c_int_p, c_int_p] + \
                 [c_double_p] * 9
             L.hprlp_b200_version.restype = C.c_char_p
+            L.hprlp_b200_solve_partitioned_synth.restype = Results
+            L.hprlp_b200_solve_partitioned_synth.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(Parameters), C.c_int,
+                                                             C.c_int, C.c_int, c_double_p, C.POINTER(B200Info)]
+            L.hprlp_b200_synth_rows.restype = C.c_int
+            L.hprlp_b200_synth_rows.argtypes = [C.c_int, C.c_int, C.c_ulonglong, C.c_longlong, C.c_int, c_int_p, c_double_p]
             L.hprlp_b200_solve_partitioned.restype = Results
             L.hprlp_b200_solve_partitioned.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_int, C.c_int, C.POINTER(B200Info)]
             L.hprlp_b200_solve_batched_multi.restype = BatchedResults
@@ -237,6 +242,24 @@ class HprLib:
         out = self._take(res, mm.m, mm.n)
         out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         return out
+
+    def solve_partitioned_synth(self, m, n, K, param, n_gpus, seed=None, want_solution=True, quiet=True):
+        info = B200Info()
+        obj = C.c_double(0.0)
+        res = self.lib.hprlp_b200_solve_partitioned_synth(int(m), int(n), int(K), SEED if seed is None else seed, C.byref(param),
+                                                          int(n_gpus), 1 if quiet else 0, 1 if want_solution else 0, C.byref(obj),
+                                                          C.byref(info))
+        out = self._take(res, int(m), int(n))
+        out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
+        out["obj_star"] = obj.value
+        return out
+
+    def synth_rows(self, n, K, row0, rows, seed=None):
+        col = np.zeros(rows * K, np.int32); val = np.zeros(rows * K)
+        rc = self.lib.hprlp_b200_synth_rows(int(n), int(K), SEED if seed is None else seed, int(row0), int(rows), _ip(col), _dp(val))
+        if rc != 0:
+            raise RuntimeError("hprlp_b200_synth_rows failed")
+        return col, val
 
     def power_start(self, m, device=0):
         out = np.zeros(m)

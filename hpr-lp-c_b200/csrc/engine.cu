@@ -413,11 +413,36 @@ void Engine::alloc_common() {
 }
 
 void Engine::upload(const LP_info_cpu *lp, int dev) {
+    prepare(lp->m, lp->n, lp->A->numElements, dev);
+    obj_constant = lp->obj_constant;
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.rowPtr, lp->A->rowPtr, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.col, lp->A->colIndex, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(A.val, lp->A->value, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(AL, lp->AL, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(AU, lp->AU, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(c, lp->c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(l, lp->l, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(u, lp->u, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+    static const bool host_transpose = getenv("HPRLP_HOST_TRANSPOSE") != nullptr;
+    if (host_transpose) {
+        std::vector<int> trp((size_t)n + 1), tci((size_t)nnz);
+        std::vector<double> tv((size_t)nnz);
+        csr_transpose_host(m, n, (int)nnz, lp->A->rowPtr, lp->A->colIndex, lp->A->value, trp.data(), tci.data(), tv.data());
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.rowPtr, trp.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.col, tci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.val, tv.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    finish_setup(!host_transpose);
+}
+
+// Device, stream, the pooled arena and every problem buffer (A, A^T, AL, AU, c, l, u); the caller then fills A and
+// the vectors (H2D copies in upload(), generator kernels in the synthetic partitioned path) and calls finish_setup().
+void Engine::prepare(int m_, int n_, long long nnz_, int dev) {
     device = dev;
     HPR_CUDA_CHECK(cudaSetDevice(device));
     HPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    m = lp->m; n = lp->n; nnz = lp->A->numElements;
-    obj_constant = lp->obj_constant;
+    m = m_; n = n_; nnz = nnz_;
     {
         // arena size: two padded CSR copies + item tables + 5 problem vectors + 9 n-vectors + 8 m-vectors + partials
         const size_t ctas = (size_t)((nnz + kChunk - 1) / kChunk) + 1, padded = ctas * kChunk, witems = ctas * kWarps;
@@ -449,34 +474,28 @@ void Engine::upload(const LP_info_cpu *lp, int dev) {
     }
     alloc_matrix(A, m, n, nnz);
     alloc_matrix(AT, n, m, nnz);
-    HPR_CUDA_CHECK(cudaMemcpyAsync(A.rowPtr, lp->A->rowPtr, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(A.col, lp->A->colIndex, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(A.val, lp->A->value, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
-    static const bool host_transpose = getenv("HPRLP_HOST_TRANSPOSE") != nullptr;
-    if (host_transpose) {
-        std::vector<int> trp((size_t)n + 1), tci((size_t)nnz);
-        std::vector<double> tv((size_t)nnz);
-        csr_transpose_host(m, n, (int)nnz, lp->A->rowPtr, lp->A->colIndex, lp->A->value, trp.data(), tci.data(), tv.data());
-        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.rowPtr, trp.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, stream));
-        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.col, tci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
-        HPR_CUDA_CHECK(cudaMemcpyAsync(AT.val, tv.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
-        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
-    } else {
-        // A^T built on the device in the reference's entry order (stable sort by column), transpose.cu
-        device_transpose_csr(m, n, (int)nnz, A.rowPtr, A.col, A.val, AT.rowPtr, AT.col, AT.val, stream);
-    }
     AL = dalloc<double>(m); AU = dalloc<double>(m); c = dalloc<double>(n); l = dalloc<double>(n); u = dalloc<double>(n);
-    HPR_CUDA_CHECK(cudaMemcpyAsync(AL, lp->AL, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(AU, lp->AU, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(c, lp->c, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(l, lp->l, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(u, lp->u, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+}
+
+// A^T on the device in the reference's entry order (stable sort by column, transpose.cu), item tables, work vectors.
+void Engine::finish_setup(bool build_transpose) {
+    if (build_transpose) device_transpose_csr(m, n, (int)nnz, A.rowPtr, A.col, A.val, AT.rowPtr, AT.col, AT.val, stream);
     finish_matrix(A);
     finish_matrix(AT);
     alloc_common();
     zo_buf = dalloc<double>(n);
     g_arena = nullptr;
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// plain SpMV helpers for setup-time use (synthetic instance generation): out = A g / out = A^T g
+void Engine::spmv_A(const double *g, double *out) {
+    SpmvOp<false> o; o.g = g; o.tex = 0; o.out = out; o.q = nullptr; o.partials = nullptr;
+    launch_stream(A, o, stream);
+}
+void Engine::spmv_AT(const double *g, double *out) {
+    SpmvOp<false> o; o.g = g; o.tex = 0; o.out = out; o.q = nullptr; o.partials = nullptr;
+    launch_stream(AT, o, stream);
 }
 
 Engine::~Engine() {

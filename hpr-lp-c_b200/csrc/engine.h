@@ -93,6 +93,10 @@ class Engine {
 
     // ---- setup (reference copy_lpinfo_to_device + allocate_memory, src/preprocess.cu:66-256) ----
     void upload(const LP_info_cpu *lp, int device);
+    void prepare(int m, int n, long long nnz, int device);   // allocate; caller fills A + vectors, then finish_setup()
+    void finish_setup(bool build_transpose);
+    void spmv_A(const double *g, double *out);
+    void spmv_AT(const double *g, double *out);
     // device-resident CSR (already on this GPU); arrays are copied into padded engine storage
     void upload_device(int m, int n, long long nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
                        const double *d_AL, const double *d_AU, const double *d_l, const double *d_u,

@@ -74,6 +74,16 @@ HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, i
 HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, const HPRLP_parameters *param, int n_gpus,
                                            int quiet, hprlp_b200_info *info);
 
+/* The synthetic "uniform" LP of BASELINE.json generated shard by shard ON the GPUs (same counter-based generator as
+ * tools/synth_lp.c, bit-identical matrix) and solved row-partitioned: the path for instances whose CSR + transpose
+ * exceed one GPU and the int32 host ABI (config 5, nnz = 6e9).  Each shard needs < 2^31 nonzeros.  *obj_star = the
+ * constructed optimal value; want_solution == 0 returns no x/y/z. */
+HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, int K, unsigned long long seed,
+                                                 const HPRLP_parameters *param, int n_gpus, int quiet, int want_solution,
+                                                 double *obj_star, hprlp_b200_info *info);
+/* Test hook: rows [row0, row0+rows) of that matrix, generated on the device, copied to host (rows*K entries each). */
+int hprlp_b200_synth_rows(int n, int K, unsigned long long seed, long long row0, int rows, int *col_out, double *val_out);
+
 /* Presolve step only (PSLP bridge, host): fills *reduced and *handle, returns 1 on success, 0 when presolve is
  * unavailable or failed (the caller then solves the original model, reference src/HPRLP.cu:508-511).
  * hprlp_b200_presolve_free releases both. */

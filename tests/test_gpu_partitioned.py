@@ -41,3 +41,31 @@ def test_partitioned_single_gpu_falls_through(pkg, engine):
     assert one["status"] == same["status"] and one["iter"] == same["iter"]
     for k in "xyz":
         assert np.array_equal(one[k], same[k])
+
+
+def test_device_generator_matches_host_generator(pkg, engine):
+    """The on-device shard generator (csrc/synth_device.cu) reproduces tools/synth_lp.c bit for bit, any row block."""
+    m, n, K = 600, 900, 40          # K/n large enough that duplicate column draws (re-draw path) occur
+    lp = pkg.synth_lp("uniform", m, n, m * K)
+    for row0, rows in ((0, m), (137, 200), (m - 1, 1)):
+        col, val = engine.synth_rows(n, K, row0, rows)
+        assert np.array_equal(col, lp["colIndex"][row0 * K:(row0 + rows) * K])
+        assert np.array_equal(val, lp["values"][row0 * K:(row0 + rows) * K])
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_device_generated_partitioned_solve_matches_host_lp(pkg, engine, gpus):
+    if _ngpu() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    m, n, K = 4000, 12000, 25
+    lp = pkg.synth_lp("uniform", m, n, m * K, with_solution=True)
+    p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-6)
+    model = engine.create_model(lp)
+    host = engine.solve(model, p, main=True)
+    engine.free_model(model)
+    dev = engine.solve_partitioned_synth(m, n, K, p, n_gpus=gpus)
+    assert abs(dev["obj_star"] - lp["obj_star"]) <= 1e-10 * (1 + abs(lp["obj_star"]))    # same LP up to rounding of c
+    assert dev["status"] == host["status"] == "OPTIMAL" and dev["iter"] == host["iter"]
+    assert abs(dev["primal_obj"] - host["primal_obj"]) <= 1e-8 * (1 + abs(host["primal_obj"]))
+    for k in "xyz":
+        assert np.max(np.abs(dev[k] - host[k])) <= 1e-6 * max(1.0, np.max(np.abs(host[k]))), k
