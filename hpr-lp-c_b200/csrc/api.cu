@@ -106,15 +106,26 @@ HPRLP_results hprlp_b200_solve_ex(const LP_info_cpu *lp, const HPRLP_parameters 
     HPRLP_parameters def;
     const HPRLP_parameters *param = param_in ? param_in : &def;
     if (!quiet) print_banner_and_params(param);
-    Engine eng;
-    SolveHooks hooks;
-    hooks.power_z0 = power_z0;
-    hooks.n_trace = n_trace; hooks.trace_iters = trace_iters;
-    hooks.trace_x = trace_x; hooks.trace_y = trace_y; hooks.trace_z = trace_z;
-    hooks.quiet = quiet != 0;
-    prepare_engine(eng, lp, param, &hooks, hooks.quiet);
-    HPRLP_results out = eng.solve(param, &hooks);
-    fill_info(eng, hooks, info);
+    static const bool timing = getenv("HPRLP_TIMING") != nullptr;   // stage wall times (with device syncs) on stderr
+    const double t0 = now_seconds();
+    double t1 = t0, t2 = t0;
+    HPRLP_results out;
+    {
+        Engine eng;
+        SolveHooks hooks;
+        hooks.power_z0 = power_z0;
+        hooks.n_trace = n_trace; hooks.trace_iters = trace_iters;
+        hooks.trace_x = trace_x; hooks.trace_y = trace_y; hooks.trace_z = trace_z;
+        hooks.quiet = quiet != 0;
+        prepare_engine(eng, lp, param, &hooks, hooks.quiet);
+        if (timing) { cudaStreamSynchronize(eng.stream); t1 = now_seconds(); }
+        out = eng.solve(param, &hooks);
+        fill_info(eng, hooks, info);
+        t2 = now_seconds();
+    }
+    if (timing)
+        std::fprintf(stderr, "[hprlp timing] upload+scale %.4f s, solve (power + loop + collect) %.4f s, teardown %.4f s\n", t1 - t0, t2 - t1,
+                     now_seconds() - t2);
     return out;
 }
 

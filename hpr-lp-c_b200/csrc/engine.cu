@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #define HPR_SET_TEX(op, t) op.tex = t;
 
@@ -232,18 +233,15 @@ static inline int vec_grid(int len) {
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 // per-CTA partial blocks written by one streamed pass: main-kernel CTAs + fix-up CTAs
-static int part_blocks(const DevCsr &M) { return M.n_items + (M.n_cut + kThreads - 1) / kThreads; }
+static int part_blocks(const DevCsr &M) { return M.n_items; }
 
 static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
-    v.head_part = M.head_part; v.tail_part = M.tail_part; v.counters = M.counters;
-    v.n_cut = M.n_cut; v.cut_row = M.cut_row; v.cut_ia = M.cut_ia; v.cut_ib = M.cut_ib;
+    v.head_part = M.head_part; v.tail_part = M.tail_part;
     return v;
 }
-
-static thread_local long long g_fixup_launches = 0;   // fix-up launches issued by launch_one (added to Engine::launches)
 
 template <class Op, int G>
 static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
@@ -258,11 +256,6 @@ static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
         configured.fetch_or(1u << dev);
     }
     csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
-    // rows cut by item boundaries: summed in item order + epilogue (stream order makes the partials visible)
-    if (v.n_cut > 0) {
-        csr_fixup_kernel<Op, int><<<(v.n_cut + kThreads - 1) / kThreads, kThreads, 0, st>>>(v, op, v.n_items);
-        g_fixup_launches++;
-    }
 }
 
 template <class Op>
@@ -311,6 +304,28 @@ static T *dalloc(size_t count) {
 }
 static void dfree(void *p) { if (p) cudaFree(p); }
 
+// Small pinned host blocks (residual scalars, sigma parameters) are recycled across solves for the life of the process:
+// cudaFreeHost synchronises the device and was measured at 0.02 - 2.5 s per call on B200 after multi-GB solves
+// (HPRLP_TIMING=1), more than the whole C2 solve.  Blocks are portable (any device), 32 doubles each.
+namespace {
+std::mutex g_pinned_mu;
+std::vector<double *> g_pinned_free;
+}
+double *pinned_block_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) { double *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+    }
+    double *p = nullptr;
+    HPR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&p), 32 * sizeof(double), cudaHostAllocPortable));
+    return p;
+}
+void pinned_block_release(double *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
+}
+
 static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -349,14 +364,12 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.val = dalloc<double>(padded);
     const size_t witems = (size_t)M.n_items * kWarps;   // warp items (n_items = CTAs)
     M.item_row = dalloc<int>(witems + 1);
-    M.head_part = dalloc<double>(witems * 2);
-    M.tail_part = dalloc<double>(witems * 2);
-    M.counters = dalloc<unsigned>(witems);
-    M.cut_row = dalloc<int>(witems); M.cut_ia = dalloc<int>(witems); M.cut_ib = dalloc<int>(witems);
+    M.head_part = dalloc<PartSlot>(witems * 2);   // zero = "not published"; consumers clear what they read
+    M.tail_part = dalloc<PartSlot>(witems * 2);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
-    dfree(M.head_part); dfree(M.tail_part); dfree(M.counters);
+    dfree(M.head_part); dfree(M.tail_part);
     M = DevCsr();
 }
 
@@ -379,10 +392,6 @@ void Engine::finish_matrix(DevCsr &M) {
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
-    // compact list of the rows cut by item boundaries (item order): flags -> exclusive scan -> scatter
-    const int n_real = (int)((M.nnz + kWarpChunk - 1) / kWarpChunk);
-    M.n_cut = build_cut_list(M.rowPtr, M.item_row, M.rows, n_real, M.cut_row, M.cut_ia, M.cut_ib, stream);
-    launches += 3;
 }
 
 void Engine::alloc_common() {
@@ -396,8 +405,8 @@ void Engine::alloc_common() {
     partial_blocks = std::max(std::max(part_blocks(A), part_blocks(AT)), kVecBlocks);
     d_partials = dalloc<double>((size_t)partial_blocks * kMaxSlots);
     d_scal = dalloc<double>(16);
-    HPR_CUDA_CHECK(cudaMallocHost(&h_scal, 16 * sizeof(double)));
-    HPR_CUDA_CHECK(cudaMallocHost(&h_params, 4 * sizeof(double)));
+    h_scal = pinned_block_acquire();      // 16 residual / reduction scalars
+    h_params = h_scal + 16;               // 4 sigma parameters (same recycled pinned block)
     auto make_tex = [](double *ptr, size_t count) {
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ptr;
         rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = count * sizeof(double);
@@ -449,7 +458,7 @@ void Engine::prepare(int m_, int n_, long long nnz_, int dev) {
         size_t need = 0;
         for (size_t rows : {(size_t)m, (size_t)n})
             need += arena_round((rows + 1) * 4) + arena_round(padded * 4) + arena_round(padded * 8) + arena_round((witems + 1) * 4) +
-                    2 * arena_round(witems * 16) + 4 * arena_round(witems * 4);
+                    2 * arena_round(witems * 2 * sizeof(PartSlot));
         need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((size_t)n * 8);
         need += arena_round((size_t)(ctas + witems / kWarps + kVecBlocks + 64) * kMaxSlots * 8) + (1u << 16);
         Arena *ar = new Arena;
@@ -499,20 +508,30 @@ void Engine::spmv_AT(const double *g, double *out) {
 }
 
 Engine::~Engine() {
+    static const bool timing = getenv("HPRLP_TIMING") != nullptr;
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    t[0] = now_seconds();
     if (stream) cudaStreamSynchronize(stream);
     for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
     graphs_.clear();
-    for (cudaTextureObject_t t : {tex_y, tex_xhat, tex_q, tex_atq})
-        if (t) cudaDestroyTextureObject(t);
+    t[1] = now_seconds();
+    for (cudaTextureObject_t tx : {tex_y, tex_xhat, tex_q, tex_atq})
+        if (tx) cudaDestroyTextureObject(tx);
+    t[2] = now_seconds();
     if (arena_) {   // every device buffer of this engine lives in the arena
         Arena *ar = static_cast<Arena *>(arena_);
         if (pooled_ && stream) { cudaFreeAsync(ar->base, stream); cudaStreamSynchronize(stream); }
         else cudaFree(ar->base);
         delete ar;
     }
-    if (h_scal) cudaFreeHost(h_scal);
-    if (h_params) cudaFreeHost(h_params);
+    t[3] = now_seconds();
+    pinned_block_release(h_scal);         // h_params lives in the same block
+    t[4] = now_seconds();
     if (stream) cudaStreamDestroy(stream);
+    t[5] = now_seconds();
+    if (timing)
+        fprintf(stderr, "[hprlp timing] teardown: graphs %.4f, textures %.4f, arena %.4f, pinned %.4f, stream %.4f s\n", t[1] - t[0],
+                t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
 }
 
 void Engine::allreduce(double *buf, size_t count, bool max_op) {
@@ -657,10 +676,22 @@ void Engine::power_start_vector(double *d_z) {
 
 double Engine::power_iteration(int max_iter, double tol, const double *host_z0, int *iters_out) {
     double *z = wm, *q = wm2, *atq = wn;
+    static const bool timing = getenv("HPRLP_TIMING") != nullptr;
+    double t_start = 0.0;
+    if (timing) { cudaStreamSynchronize(stream); t_start = now_seconds(); }
     if (host_z0) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(z, host_z0, sizeof(double) * m, cudaMemcpyHostToDevice, stream));
     } else {
         power_start_vector(z);
+    }
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    double t_sync = 0.0, t_sync_max = 0.0;
+    if (timing) {
+        cudaStreamSynchronize(stream);
+        fprintf(stderr, "[hprlp timing] power start vector %.4f s\n", now_seconds() - t_start);
+        t_start = now_seconds();
+        cudaEventCreate(&pe0); cudaEventCreate(&pe1);
+        cudaEventRecord(pe0, stream);
     }
     // d_scal[0] = <z,z>, d_scal[1] = <q,z>, d_scal[2] = |z - lambda q|^2
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, m, d_partials);
@@ -684,7 +715,9 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
             final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
             launches += 2;
             allreduce(d_scal + 2, 1);
+            const double ts0 = timing ? now_seconds() : 0.0;
             fetch_scalars(3);
+            if (timing) { const double d = now_seconds() - ts0; t_sync += d; t_sync_max = std::max(t_sync_max, d); }
             lambda = h_scal[1];
             if (sqrt(h_scal[2]) < tol) break;
         }
@@ -696,6 +729,13 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     }
     if (iters_out) *iters_out = it;
     HPR_CUDA_CHECK(cudaGetLastError());
+    if (timing) {
+        float dev_ms = 0.f;
+        cudaEventRecord(pe1, stream); cudaEventSynchronize(pe1); cudaEventElapsedTime(&dev_ms, pe0, pe1);
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+        fprintf(stderr, "[hprlp timing] power loop %d iterations: wall %.4f s, device %.4f s, in syncs %.4f s (max %.4f s)\n", it,
+                now_seconds() - t_start, dev_ms * 1e-3, t_sync, t_sync_max);
+    }
     return lambda;
 }
 
@@ -781,17 +821,16 @@ void Engine::run_normal(int count) {
                 cudaGraph_t g = nullptr;
                 cudaGraphExec_t ge = nullptr;
                 HPR_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                const long long before = launches, before_fix = g_fixup_launches;
+                const long long before = launches;
                 for (int i = 0; i < len; ++i) launch_iteration(false);
                 launches = before;
-                g_fixup_launches = before_fix;
                 HPR_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
                 HPR_CUDA_CHECK(cudaGraphInstantiate(&ge, g, nullptr, nullptr, 0));
                 cudaGraphDestroy(g);
                 it = graphs_.emplace(len, ge).first;
             }
             HPR_CUDA_CHECK(cudaGraphLaunch(it->second, stream));
-            launches += 4LL * len;
+            launches += 2LL * len;
         }
         count -= len;
     }
@@ -1148,7 +1187,7 @@ void Engine::fill_hooks(SolveHooks *hooks) {
     hooks->lambda_max = lambda_max;
     hooks->sigma = sigma;
     hooks->restarts = loop.rs.times;
-    hooks->kernel_launches = launches + g_fixup_launches;
+    hooks->kernel_launches = launches;
     hooks->scal[0] = b_scale; hooks->scal[1] = c_scale; hooks->scal[2] = norm_b; hooks->scal[3] = norm_c;
     hooks->scal[4] = norm_b_org; hooks->scal[5] = norm_c_org;
 }

@@ -25,6 +25,11 @@ namespace hpr {
         }                                                                                     \
     } while (0)
 
+#ifndef HPR_PARTSLOT_DEFINED
+#define HPR_PARTSLOT_DEFINED
+struct alignas(16) PartSlot { double v; unsigned long long ready; };   // one published partial sum (kernels.cuh)
+#endif
+
 // Device CSR matrix + the item decomposition used by csr_stream_kernel.
 struct DevCsr {
     int rows = 0, cols = 0;
@@ -34,10 +39,7 @@ struct DevCsr {
     double *val = nullptr;  // padded likewise
     int *item_row = nullptr;
     int n_items = 0;
-    double *head_part = nullptr, *tail_part = nullptr;
-    unsigned *counters = nullptr;
-    int n_cut = 0;          // rows cut by warp-item boundaries
-    int *cut_row = nullptr, *cut_ia = nullptr, *cut_ib = nullptr;
+    PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
@@ -174,9 +176,6 @@ void csr_transpose_host(int rows, int cols, int nnz, const int *rp, const int *c
 
 void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
                           int *d_trp, int *d_tcol, double *d_tval, cudaStream_t st);
-
-int build_cut_list(const int *d_rowPtr, const int *d_item_row, int rows, int n_real_items, int *cut_row, int *cut_ia,
-                   int *cut_ib, cudaStream_t st);
 
 // presolve bridge (presolve.cpp); returns false when unavailable / failed (caller solves the original model)
 bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);

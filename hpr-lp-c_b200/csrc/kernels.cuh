@@ -17,9 +17,12 @@
 //           the product array; the row totals are handed to one lane per row, so that the fused
 //           epilogue (projection, dual update, Halpern averaging, residual terms ...) runs
 //           lane-parallel over consecutive rows with coalesced vector loads/stores.
-//   rows cut by an item boundary publish a partial sum; the last contributor to arrive (one
-//           atomic counter per row end) adds the partials in a fixed order and runs the epilogue --
-//           deterministic, and no second "fix-up" launch.
+//   rows cut by an item boundary: every item but the last one of the row publishes its partial sum as one
+//           16-byte {value, ready} packet; the warp whose item holds the END of the row waits for the packets of
+//           the items to its left (they belong to lower-numbered warps of the same CTA or to lower-numbered,
+//           i.e. earlier dispatched, CTAs: the in-order "look-back" used by single-pass scans), adds them in item
+//           order, runs the epilogue and clears the packets for the next launch.  No second launch, no atomics,
+//           no fences, and the summation order is fixed, so results are bitwise run-to-run reproducible.
 //
 // Replaces, on the iteration path, the reference's fused_update_* kernels
 // (src/cuda_kernels/HPR_cuda_kernels.cu:297-427), its cuSPARSE SpMV + elementwise kernels
@@ -41,7 +44,7 @@ constexpr int kWarps = kThreads / 32;
 #define HPR_ROUND_NNZ 8
 #endif
 #ifndef HPR_MIN_BLOCKS
-#define HPR_MIN_BLOCKS 8
+#define HPR_MIN_BLOCKS 6
 #endif
 #ifndef HPR_TEX_GATHER
 #define HPR_TEX_GATHER 1
@@ -53,6 +56,11 @@ constexpr int kChunk = kWarps * kWarpChunk;     // nonzeros per CTA (array paddi
 constexpr int kMaxSlots = 8;                    // reduction slots per CTA
 constexpr int kSeqPartials = 8;                 // split rows with more partials are summed by the whole warp
 
+#ifndef HPR_PARTSLOT_DEFINED
+#define HPR_PARTSLOT_DEFINED
+struct alignas(16) PartSlot { double v; unsigned long long ready; };   // one published partial sum (see part_publish)
+#endif
+
 template <typename RP>
 struct CsrView {
     int rows;
@@ -62,13 +70,39 @@ struct CsrView {
     const double *val;    // padded likewise
     const int *item_row;  // n_ctas*kWarps + 1 entries: first row finalised by warp item i
     int n_items;          // CTAs in the grid
-    double *head_part;    // [items * 2] partial of the row entering the item from the left
-    double *tail_part;    // [items * 2] partial of the row leaving the item to the right
-    unsigned *counters;   // unused since r1 v2 (kept for layout stability)
-    // rows cut by item boundaries, in item order (built once at setup): row, first and last item it spans
-    int n_cut;
-    const int *cut_row, *cut_ia, *cut_ib;
+    PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
+    PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
 };
+
+// Publish / consume one partial sum.  Value and ready flag travel in ONE aligned 16-byte access, so no fence is needed
+// between them; the consumer clears the packet (all packets are zero between launches).
+__device__ __forceinline__ void part_publish(PartSlot *p, double v) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(1ll) : "memory");
+}
+__device__ __forceinline__ double part_consume(PartSlot *p) {
+    long long a, f;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(f) : "l"(p) : "memory");
+        if (f != 0) break;
+        __nanosleep(64);   // every poll is a request on the L1->crossbar port, the unit that bounds this kernel
+    }
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(0ll) : "memory");
+    return __longlong_as_double(a);
+}
+// The same hand-off between two warps of one CTA goes through shared memory (7 of 8 cut rows): no L2 round trip.
+__device__ __forceinline__ void part_publish_cta(PartSlot *p, double v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(a), "l"(__double_as_longlong(v)), "l"(1ll) : "memory");
+}
+__device__ __forceinline__ double part_consume_cta(PartSlot *p) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+    long long a, f;
+    do {
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(f) : "r"(s) : "memory");
+    } while (f == 0);
+    asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %1};" ::"r"(s), "l"(0ll) : "memory");
+    return __longlong_as_double(a);
+}
 
 __device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
 __device__ __forceinline__ int2 ld_stream(const int2 *p) { return __ldcs(p); }
@@ -124,9 +158,15 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *prod = smem + (size_t)warp * NV * kWarpChunk;            // [NV][kWarpChunk], private to this warp
     double *red_scratch = smem + (size_t)kWarps * NV * kWarpChunk;
+    __shared__ double own_part[kWarps * 2];     // [warp][2]: this item's share of the row it finishes
+    __shared__ PartSlot cta_part[kWarps * 4];   // [warp][head, tail][2]: partials handed to a warp of this CTA
+    if (threadIdx.x < kWarps * 4) { cta_part[threadIdx.x].v = 0.0; cta_part[threadIdx.x].ready = 0ull; }
+    __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
 
     op.init();
     const int item = blockIdx.x * kWarps + warp;
+    const int cta_item0 = blockIdx.x * kWarps;
+    const long long cta_end = ((long long)blockIdx.x + 1) * kChunk;   // a row with p1 <= cta_end ends inside this CTA
     const long long s = (long long)item * kWarpChunk;
     const long long e = (s + kWarpChunk < M.nnz) ? s + kWarpChunk : (s < M.nnz ? M.nnz : s);
 
@@ -218,20 +258,70 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
             }
         }
 
-        // lane-parallel epilogue.  Rows cut by an item boundary only publish their partial sum here (plain
-        // stores, no fence, no atomic); csr_fixup_kernel, launched right after on the same stream, adds the
-        // partials of each cut row in item order and runs its epilogue -- deterministic by construction.
+        // lane-parallel epilogue.  A row cut by an item boundary is finished by the item that holds its end (below);
+        // the other items it spans only publish their partial sums.
         if (valid) {
-            const bool head = (r == rA) && (p0 < s);   // row entered this item from the left
+            const bool head = (r == rA) && (p0 < s);   // row entered this item from the left (lane 0, first batch)
             const bool cont = (p1 > e);                // row continues to the right
             if (!head && !cont) {
                 op.row(r, tot, p0, p1);
-            } else if (head || p0 < e) {               // (else: r == rB and it starts in a later item)
-                double *slot = (head ? M.head_part : M.tail_part) + (size_t)item * 2;
+            } else if (head && !cont) {                // finished below; park this item's share (no live registers)
 #pragma unroll
-                for (int q = 0; q < NV; ++q) slot[q] = tot[q];
+                for (int q = 0; q < NV; ++q) own_part[warp * 2 + q] = tot[q];
+            } else if (head || p0 < e) {               // (else: r == rB and it starts in a later item)
+                if (p1 <= cta_end) {                   // finished by a later warp of this CTA
+                    PartSlot *slot = cta_part + warp * 4 + (head ? 0 : 2);
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) part_publish_cta(slot + q, tot[q]);
+                } else {                               // finished by a later CTA
+                    PartSlot *slot = (head ? M.head_part : M.tail_part) + (size_t)item * 2;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) part_publish(slot + q, tot[q]);
+                }
             }
         }
+    }
+
+    // ---- the row that ends here after entering from the left: total = tail[ia] + head[ia+1] + ... + head[ib-1] + own,
+    // in item order (kSeqPartials or more partials: stride-32 order + xor tree).  Done last, after this item has published
+    // everything other warps may be waiting for.  The lanes fetch the partials in parallel (one wait, not one per partial).
+    long long P0 = 0, P1 = 0;
+    if (rA <= r_last) { P0 = (long long)M.rowPtr[rA]; P1 = (long long)M.rowPtr[rA + 1]; }   // warp-uniform reload
+    if (rA <= r_last && P0 < s && P1 <= e) {
+        __syncwarp();   // own_part written by lane 0 above
+        const int ia = (int)(P0 / kWarpChunk), ib = item;
+        auto fetch = [&](int j, bool tail, int q) -> double {   // partial of item j: same CTA -> shared, earlier CTA -> global
+            if (j >= cta_item0) return part_consume_cta(cta_part + (j - cta_item0) * 4 + (tail ? 2 : 0) + q);
+            return part_consume((tail ? M.tail_part : M.head_part) + (size_t)j * 2 + q);
+        };
+        double sum[NV];
+        if (ib - ia < kSeqPartials) {
+            double v[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) v[q] = (ia + lane < ib) ? fetch(ia + lane, lane == 0, q) : own_part[warp * 2 + q];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = __shfl_sync(0xffffffffu, v[q], 0);
+            for (int t = 1; t <= ib - ia; ++t) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_sync(0xffffffffu, v[q], t));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = 0.0;
+            for (int j = ia + lane; j <= ib; j += 32) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const double v = (j == ib) ? own_part[warp * 2 + q] : fetch(j, j == ia, q);
+                    sum[q] = combine<MX>(sum[q], v);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
+            }
+        }
+        if (lane == 0) op.row(rA, sum, P0, P1);
     }
     op.finish(red_scratch, blockIdx.x);
 }
@@ -254,89 +344,6 @@ __global__ void build_item_rows_kernel(const RP *rowPtr, int rows, long long nnz
     item_row[i] = lo;
 }
 
-
-// Finalises the rows cut by item boundaries, one cut row per lane from the compact list built at setup
-// (cut_row/cut_ia/cut_ib, item order): total = tail[ia] + head[ia+1] + ... + head[ib]; rows with more than
-// kSeqPartials partials are summed by the whole warp (stride-32 order + xor tree).  The list, the partials, the row
-// pointers and the epilogue inputs are independent loads: two memory latencies instead of the four of a
-// item_row -> rowPtr -> partial -> vector chain.  Partial-sum blocks of reducing ops go to
-// partials[(block_offset + blockIdx.x)].  Not launched at all when the matrix has no cut rows.
-template <class Op, typename RP>
-__global__ void __launch_bounds__(kThreads) csr_fixup_kernel(CsrView<RP> M, Op op, int block_offset) {
-    constexpr int NV = Op::NV;
-    constexpr bool MX = Op::kMax;
-    __shared__ double red_scratch[kMaxSlots * kWarps];
-    const int lane = threadIdx.x & 31;
-    op.init();
-    const int k = blockIdx.x * kThreads + threadIdx.x;
-    int coop = 0, ia = 0, ib = 0, r = 0;
-    long long p0 = 0, p1 = 0;
-    if (k < M.n_cut) {
-        r = __ldg(M.cut_row + k);
-        ia = __ldg(M.cut_ia + k);
-        ib = __ldg(M.cut_ib + k);
-        p0 = (long long)M.rowPtr[r];
-        p1 = (long long)M.rowPtr[r + 1];
-        if (ib - ia < kSeqPartials) {
-            double sum[NV];
-#pragma unroll
-            for (int q = 0; q < NV; ++q) sum[q] = M.tail_part[(size_t)ia * 2 + q];
-            for (int j = ia + 1; j <= ib; ++j) {
-#pragma unroll
-                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], M.head_part[(size_t)j * 2 + q]);
-            }
-            op.row(r, sum, p0, p1);
-        } else {
-            coop = 1;
-        }
-    }
-    unsigned pend = __ballot_sync(0xffffffffu, coop);
-    while (pend) {
-        const int src = __ffs(pend) - 1;
-        const int a = __shfl_sync(0xffffffffu, ia, src);
-        const int b = __shfl_sync(0xffffffffu, ib, src);
-        double sum[NV];
-#pragma unroll
-        for (int q = 0; q < NV; ++q) sum[q] = 0.0;
-        for (int j = a + lane; j <= b; j += 32) {
-            const double *srcp = ((j == a) ? M.tail_part : M.head_part) + (size_t)j * 2;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], srcp[q]);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-            for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
-        }
-        if (lane == src) op.row(r, sum, p0, p1);
-        pend &= pend - 1;
-    }
-    op.finish(red_scratch, block_offset + blockIdx.x);
-}
-
-// Setup: flag[i] = 1 when warp item i finalises a cut row (its first row entered from the left and ends inside it);
-// after an exclusive scan of the flags, scatter (row, first item, last item) into the compact list in item order.
-template <typename RP>
-__global__ void cut_flags_kernel(const RP *rowPtr, const int *item_row, int rows, int n_real_items, int *flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_real_items) return;
-    int f = 0;
-    if (i > 0) {
-        const int r = item_row[i];
-        if (r < rows && item_row[i + 1] > r && (long long)rowPtr[r] < (long long)i * kWarpChunk) f = 1;
-    }
-    flag[i] = f;
-}
-template <typename RP>
-__global__ void cut_scatter_kernel(const RP *rowPtr, const int *item_row, const int *flag, const int *pos, int n_real_items,
-                                   int *cut_row, int *cut_ia, int *cut_ib) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_real_items || !flag[i]) return;
-    const int r = item_row[i];
-    cut_row[pos[i]] = r;
-    cut_ia[pos[i]] = (int)((long long)rowPtr[r] / kWarpChunk);
-    cut_ib[pos[i]] = i;
-}
 
 // ================================================================================================
 // Ops

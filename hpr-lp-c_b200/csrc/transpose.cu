@@ -70,27 +70,4 @@ void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, cons
     cudaFreeAsync(rowid, st); cudaFreeAsync(idx, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(perm, st); cudaFreeAsync(tmp, st);
 }
 
-// Compact, item-ordered list of the rows cut by warp-item boundaries (setup; see csr_fixup_kernel).  Returns the count.
-int build_cut_list(const int *d_rowPtr, const int *d_item_row, int rows, int n_real_items, int *cut_row, int *cut_ia,
-                   int *cut_ib, cudaStream_t st) {
-    if (n_real_items <= 1) return 0;
-    int *flag = nullptr, *pos = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&flag), sizeof(int) * (size_t)n_real_items, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&pos), sizeof(int) * (size_t)n_real_items, st));
-    const int T = 256, G = (n_real_items + T - 1) / T;
-    cut_flags_kernel<int><<<G, T, 0, st>>>(d_rowPtr, d_item_row, rows, n_real_items, flag);
-    HPR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, pos, n_real_items, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
-    HPR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, pos, n_real_items, st));
-    cut_scatter_kernel<int><<<G, T, 0, st>>>(d_rowPtr, d_item_row, flag, pos, n_real_items, cut_row, cut_ia, cut_ib);
-    int last_flag = 0, last_pos = 0;
-    HPR_CUDA_CHECK(cudaMemcpyAsync(&last_flag, flag + n_real_items - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(&last_pos, pos + n_real_items - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    HPR_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFreeAsync(flag, st); cudaFreeAsync(pos, st); cudaFreeAsync(tmp, st);
-    return last_pos + last_flag;
-}
-
 }  // namespace hpr
