@@ -294,9 +294,13 @@ def run_batched(args, pkg, spec, lib, rank, world, local, dist, impl):
     return out
 
 
-def steady_state_rate(pkg, lib, lp, local, k1=1000, k2=3000):
+def steady_state_rate(pkg, lib, lp, local, k1=1000, k2=None):
     """Loop iterations/s of a library that can only be driven through solve(): difference of the library's own
-    results.time between max_iter=k2 and max_iter=k1 (setup, power iteration and the reference's autotune cancel)."""
+    results.time between max_iter=k2 and max_iter=k1 (setup, power iteration and the reference's autotune cancel).
+    The span k2-k1 is sized so the difference is seconds, not tenths (the reference's power iteration + autotune vary by
+    ~0.1 s between runs: a 2000-iteration span on the nnz=1e7 LP once read 10.5k it/s against 5.1k in another run)."""
+    if k2 is None:
+        k2 = k1 + (2000 if int(lp["values"].shape[0]) >= 50_000_000 else 20000)
     ts = []
     for k in (k1, k2):
         param = pkg.Parameters.default(stop_tol=0.0, max_iter=k, use_presolve=False, device_number=local)
@@ -380,7 +384,7 @@ def main():
         out = dict(impl="reference", metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
                    value=rate, unit="HPR iterations/s", n_gpus=1, steps=len(runs), warmup=0,
                    ms_per_step=1e3 * ITERS_PER_STEP / rate, steady_state=dict(
-                       how="(3000-1000) iterations / (results.time[max_iter=3000] - results.time[max_iter=1000])", times=rate_ts), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                       how="(k2-k1) iterations / (results.time[max_iter=k2] - results.time[max_iter=k1]), k1=1000, k2-k1=2000 (nnz>=5e7) or 20000", times=rate_ts), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                    data="synthetic", config=dict(workload=spec["name"], m=lp["m"], n=lp["n"], nnz=int(lp["values"].shape[0]),
                                                  note="value = steady-state loop rate from two max_iter runs; e2e = one solve() call to KKT<1e-4 through the reference's own C API"),
                    cpu_baseline=dict(value=best["value"], unit="HPR iterations/s", cores=0, kind="reference",
