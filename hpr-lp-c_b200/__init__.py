@@ -83,7 +83,8 @@ class B200Info(C.Structure):
                 ("kernel_launches", C.c_longlong),
                 ("b_scale", C.c_double), ("c_scale", C.c_double), ("norm_b", C.c_double), ("norm_c", C.c_double),
                 ("norm_b_org", C.c_double), ("norm_c_org", C.c_double),
-                ("lanes_A", C.c_int), ("lanes_AT", C.c_int), ("items_A", C.c_int), ("items_AT", C.c_int)]
+                ("lanes_A", C.c_int), ("lanes_AT", C.c_int), ("items_A", C.c_int), ("items_AT", C.c_int),
+                ("bands_A", C.c_int), ("reserved0", C.c_int)]
 
 
 REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve", "free_model",

@@ -79,6 +79,7 @@ void fill_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info) {
     info->b_scale = h.scal[0]; info->c_scale = h.scal[1]; info->norm_b = h.scal[2]; info->norm_c = h.scal[3];
     info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
     info->lanes_A = eng.A.G; info->lanes_AT = eng.AT.G; info->items_A = eng.A.n_items; info->items_AT = eng.AT.n_items;
+    info->bands_A = (int)eng.A.bands.size(); info->reserved0 = 0;
 }
 
 }  // namespace

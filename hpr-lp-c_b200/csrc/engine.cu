@@ -251,13 +251,14 @@ static inline int vec_grid(int len) {
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 // per-CTA partial blocks written by one streamed pass: main-kernel CTAs + fix-up CTAs
-static int part_blocks(const DevCsr &M) { return M.n_items; }
+static int part_blocks(const DevCsr &M) { return M.bands.empty() ? M.n_items : M.bands.back().n_items; }
 
 static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
     v.head_part = M.head_part; v.tail_part = M.tail_part;
+    v.carry_in = nullptr; v.carry_out = nullptr;
     return v;
 }
 
@@ -277,9 +278,8 @@ static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
 }
 
 template <class Op>
-static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
-    const CsrView<int> v = view_of(M);
-    switch (M.G) {
+static void dispatch_hot(const CsrView<int> &v, int G, const Op &op, cudaStream_t st) {
+    switch (G) {
         case 1:  launch_one<Op, 1>(v, op, st); break;
         case 2:  launch_one<Op, 2>(v, op, st); break;
         case 4:  launch_one<Op, 4>(v, op, st); break;
@@ -290,11 +290,37 @@ static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
 }
 // setup / check-iteration passes: fewer instantiations
 template <class Op>
+static void dispatch_cold(const CsrView<int> &v, int G, const Op &op, cudaStream_t st) {
+    if (G <= 2)      launch_one<Op, 1>(v, op, st);
+    else if (G <= 8) launch_one<Op, 4>(v, op, st);
+    else             launch_one<Op, 16>(v, op, st);
+}
+// A pass over a column-banded matrix: one launch per band, row sums carried from band to band, the op's epilogue (and its
+// reductions) only in the last one.  The gathered slice of every launch fits the L2.
+template <class Op, bool HOT>
+static void launch_banded(const DevCsr &M, const Op &op, cudaStream_t st) {
+    static_assert(Op::NV == 1 && !Op::kMax, "banded passes carry one sum per row");
+    const int nb = (int)M.bands.size();
+    for (int b = 0; b < nb; ++b) {
+        CsrView<int> v = view_of(M.bands[b]);
+        v.carry_in = b > 0 ? M.carry : nullptr;
+        v.carry_out = b + 1 < nb ? M.carry : nullptr;
+        if (HOT) dispatch_hot(v, M.bands[b].G, op, st); else dispatch_cold(v, M.bands[b].G, op, st);
+    }
+}
+template <class Op>
+static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
+    if constexpr (Op::NV == 1 && !Op::kMax) {
+        if (!M.bands.empty()) { launch_banded<Op, true>(M, op, st); return; }
+    }
+    dispatch_hot(view_of(M), M.G, op, st);
+}
+template <class Op>
 static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
-    const CsrView<int> v = view_of(M);
-    if (M.G <= 2)      launch_one<Op, 1>(v, op, st);
-    else if (M.G <= 8) launch_one<Op, 4>(v, op, st);
-    else               launch_one<Op, 16>(v, op, st);
+    if constexpr (Op::NV == 1 && !Op::kMax) {
+        if (!M.bands.empty()) { launch_banded<Op, false>(M, op, st); return; }
+    }
+    dispatch_cold(view_of(M), M.G, op, st);
 }
 
 // One device arena per engine: a single cudaMalloc + one zero-fill instead of ~45 cudaMalloc/cudaMemset/cudaFree
@@ -410,6 +436,67 @@ void Engine::finish_matrix(DevCsr &M) {
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
+}
+
+// Column bands of M for passes whose gathered vector (M.cols doubles) does not fit the L2: 8-byte gathers from DRAM run at
+// 65 G/s against 278 G/s from the L2 (profiles/r1_gather_ceiling.json, 400 MB vs 8-40 MB vectors).  Each band is a CSR
+// matrix over all rows with the entries of one column slice (global column indices, original order inside a row).
+void Engine::build_bands(DevCsr &M) {
+    long long band_cols = 0;
+    if (const char *e = getenv("HPRLP_BAND_COLS")) band_cols = atoll(e);          // tests / tuning
+    else if ((size_t)M.cols * sizeof(double) > ((size_t)64 << 20)) band_cols = 4 << 20;   // > 64 MB: 32 MB slices
+    if (band_cols <= 0 || band_cols >= M.cols || M.nnz == 0) return;
+    int nb = (int)((M.cols + band_cols - 1) / band_cols);
+    if (nb > 64) { band_cols = (M.cols + 63) / 64; nb = (int)((M.cols + band_cols - 1) / band_cols); }
+    const size_t stride = (size_t)M.rows + 1;
+    int *brp = nullptr;
+    HPR_CUDA_CHECK(cudaMalloc(&brp, sizeof(int) * stride * nb));
+    HPR_CUDA_CHECK(cudaMemsetAsync(brp, 0, sizeof(int) * stride * nb, stream));
+    std::vector<long long> bn(nb, 0);
+    band_count(M.rows, M.rowPtr, M.col, (int)band_cols, nb, brp, bn.data(), stream);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t total = 0;
+    std::vector<size_t> o_col(nb), o_val(nb), o_item(nb), o_head(nb), o_tail(nb);
+    std::vector<int> items(nb);
+    for (int b = 0; b < nb; ++b) {
+        items[b] = std::max(1, (int)((bn[b] + kChunk - 1) / kChunk));
+        const size_t padded = (size_t)items[b] * kChunk, wit = (size_t)items[b] * kWarps;
+        o_col[b] = total;  total += up(padded * sizeof(int));
+        o_val[b] = total;  total += up(padded * sizeof(double));
+        o_item[b] = total; total += up((wit + 1) * sizeof(int));
+        o_head[b] = total; total += up(wit * 2 * sizeof(PartSlot));
+        o_tail[b] = total; total += up(wit * 2 * sizeof(PartSlot));
+    }
+    const size_t o_carry = total; total += up((size_t)M.rows * sizeof(double));
+    const size_t o_ptrs = total;  total += up(sizeof(void *) * 2 * nb);
+    char *store = nullptr;
+    HPR_CUDA_CHECK(cudaMalloc(&store, total));
+    HPR_CUDA_CHECK(cudaMemsetAsync(store, 0, total, stream));   // padding entries (col 0, value 0), packets "not published"
+    std::vector<void *> ptrs(2 * nb);
+    M.bands.assign(nb, DevCsr());
+    for (int b = 0; b < nb; ++b) {
+        DevCsr &Bd = M.bands[b];
+        Bd.rows = M.rows; Bd.cols = M.cols; Bd.nnz = bn[b]; Bd.n_items = items[b];
+        Bd.rowPtr = brp + (size_t)b * stride;
+        Bd.col = reinterpret_cast<int *>(store + o_col[b]);
+        Bd.val = reinterpret_cast<double *>(store + o_val[b]);
+        Bd.item_row = reinterpret_cast<int *>(store + o_item[b]);
+        Bd.head_part = reinterpret_cast<PartSlot *>(store + o_head[b]);
+        Bd.tail_part = reinterpret_cast<PartSlot *>(store + o_tail[b]);
+        ptrs[b] = Bd.col; ptrs[nb + b] = Bd.val;
+    }
+    HPR_CUDA_CHECK(cudaMemcpyAsync(store + o_ptrs, ptrs.data(), sizeof(void *) * 2 * nb, cudaMemcpyHostToDevice, stream));
+    band_fill(M.rows, M.rowPtr, M.col, M.val, (int)band_cols, nb, brp, reinterpret_cast<int *const *>(store + o_ptrs),
+              reinterpret_cast<double *const *>(store + o_ptrs) + nb, stream);
+    HPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // ptrs (host vector) must outlive the copy
+    for (int b = 0; b < nb; ++b) {
+        finish_matrix(M.bands[b]);
+        M.bands[b].G = pick_lanes(M.bands[b].mean_len, "HPRLP_LANES_BAND");
+    }
+    M.carry = reinterpret_cast<double *>(store + o_carry);
+    M.band_store = store;
+    M.band_rowptr_store = brp;
+    launches += 2;
 }
 
 void Engine::alloc_common() {
@@ -536,7 +623,12 @@ Engine::~Engine() {
     for (cudaTextureObject_t tx : {tex_y, tex_xhat, tex_q, tex_atq})
         if (tx) cudaDestroyTextureObject(tx);
     t[2] = now_seconds();
-    if (arena_) {   // every device buffer of this engine lives in the arena
+    for (DevCsr *M : {&A, &AT}) {
+        if (M->band_store) cudaFree(M->band_store);
+        if (M->band_rowptr_store) cudaFree(M->band_rowptr_store);
+        M->bands.clear();
+    }
+    if (arena_) {   // every device buffer of this engine lives in the arena (the column bands above excepted)
         Arena *ar = static_cast<Arena *>(arena_);
         if (pooled_ && stream) { cudaFreeAsync(ar->base, stream); cudaStreamSynchronize(stream); }
         else cudaFree(ar->base);
@@ -658,6 +750,7 @@ void Engine::scale(const HPRLP_parameters *p) {
     norm_b = nb;
     norm_c = nc;
     HPR_CUDA_CHECK(cudaGetLastError());
+    build_bands(A);   // after scaling: the bands copy the final values (no-op unless n doubles exceed the L2 budget)
 }
 
 // ------------------------------------------------------------------------------------------------

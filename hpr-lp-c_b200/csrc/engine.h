@@ -43,6 +43,12 @@ struct DevCsr {
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
+    // Column bands (Engine::build_bands): when the gathered vector is larger than the L2 can hold, the passes over this
+    // matrix run band by band over column slices that do fit, carrying the row sums in `carry` (rows doubles).
+    std::vector<DevCsr> bands;
+    double *carry = nullptr;
+    void *band_store = nullptr;   // one allocation behind all band arrays
+    void *band_rowptr_store = nullptr;
 };
 
 struct RestartState {   // reference HPRLP_restart, include/structs.h:215-228
@@ -164,6 +170,7 @@ class Engine {
    private:
     void alloc_common();
     void finish_matrix(DevCsr &M);
+    void build_bands(DevCsr &M);
     void fetch_scalars(int count);
     std::map<int, cudaGraphExec_t> graphs_;
 };
@@ -173,6 +180,11 @@ void free_lp_info_cpu(LP_info_cpu *lp);
 bool build_model_from_mps(const char *path, LP_info_cpu *lp);
 void csr_transpose_host(int rows, int cols, int nnz, const int *rp, const int *ci, const double *v,
                         int *trp, int *tci, double *tv);
+
+void band_count(int rows, const int *d_rowPtr, const int *d_col, int band_cols, int n_bands, int *band_rowPtr,
+                long long *band_nnz, cudaStream_t st);
+void band_fill(int rows, const int *d_rowPtr, const int *d_col, const double *d_val, int band_cols, int n_bands,
+               const int *band_rowPtr, int *const *d_bcol, double *const *d_bval, cudaStream_t st);
 
 void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
                           int *d_trp, int *d_tcol, double *d_tval, cudaStream_t st);

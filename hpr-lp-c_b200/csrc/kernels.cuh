@@ -72,6 +72,11 @@ struct CsrView {
     int n_items;          // CTAs in the grid
     PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
     PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
+    // Column-banded matrices (engine.cu, build_bands): a pass over the matrix is one launch per band; every band but the
+    // last stores its row sums (+ those of the bands before it) in carry_out instead of running the epilogue, the last
+    // band adds carry_in to its own row sums first.  Both null for an ordinary matrix.  Single-product ops only.
+    const double *carry_in;
+    double *carry_out;
 };
 
 // Publish / consume one partial sum.  Value and ready flag travel in ONE aligned 16-byte access, so no fence is needed
@@ -164,6 +169,11 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
 
     op.init();
+    auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
+        if (M.carry_in) t[0] += M.carry_in[r];
+        if (M.carry_out) M.carry_out[r] = t[0];
+        else op.row(r, t, q0, q1);
+    };
     const int item = blockIdx.x * kWarps + warp;
     const int cta_item0 = blockIdx.x * kWarps;
     const long long cta_end = ((long long)blockIdx.x + 1) * kChunk;   // a row with p1 <= cta_end ends inside this CTA
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
             const bool head = (r == rA) && (p0 < s);   // row entered this item from the left (lane 0, first batch)
             const bool cont = (p1 > e);                // row continues to the right
             if (!head && !cont) {
-                op.row(r, tot, p0, p1);
+                complete_row(r, tot, p0, p1);
             } else if (head && !cont) {                // finished below; park this item's share (no live registers)
 #pragma unroll
                 for (int q = 0; q < NV; ++q) own_part[warp * 2 + q] = tot[q];
@@ -321,9 +331,9 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
                 for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
             }
         }
-        if (lane == 0) op.row(rA, sum, P0, P1);
+        if (lane == 0) complete_row(rA, sum, P0, P1);
     }
-    op.finish(red_scratch, blockIdx.x);
+    if (!M.carry_out) op.finish(red_scratch, blockIdx.x);   // (warp-uniform: kernel argument)
 }
 
 // item_row[i] = first row finalised by warp item i = first r with rowPtr[r+1] > i*kWarpChunk (item 0 also owns

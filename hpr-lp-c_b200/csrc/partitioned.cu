@@ -64,7 +64,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, 
     std::vector<HPRLP_results> results(P);
     std::vector<SolveHooks> hooks(P);
     std::vector<std::string> errors(P);
-    std::vector<int> lanes(2 * P, 0);
+    std::vector<int> lanes(2 * P, 0), nbands(P, 0);
     std::vector<std::thread> workers;
     for (int p = 0; p < P; ++p) {
         workers.emplace_back([&, p]() {
@@ -86,7 +86,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, 
                 eng.upload(&shard, devs[p]);
                 eng.scale(&pp);
                 results[p] = eng.solve(&pp, &hooks[p]);
-                lanes[2 * p] = eng.A.G; lanes[2 * p + 1] = eng.AT.G;
+                lanes[2 * p] = eng.A.G; lanes[2 * p + 1] = eng.AT.G; nbands[p] = (int)eng.A.bands.size();
             } catch (const std::exception &e) {
                 errors[p] = e.what();
             }
@@ -112,7 +112,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, 
         info->restarts = h.restarts; info->power_iters = h.power_iters; info->kernel_launches = h.kernel_launches;
         info->b_scale = h.scal[0]; info->c_scale = h.scal[1]; info->norm_b = h.scal[2]; info->norm_c = h.scal[3];
         info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
-        info->lanes_A = lanes[0]; info->lanes_AT = lanes[1]; info->items_A = P; info->items_AT = P;
+        info->lanes_A = lanes[0]; info->lanes_AT = lanes[1]; info->items_A = P; info->items_AT = P; info->bands_A = nbands[0]; info->reserved0 = 0;
     }
     return out;
 }

@@ -177,6 +177,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, 
     std::vector<HPRLP_results> results(P);
     std::vector<SolveHooks> hooks(P);
     std::vector<std::string> errors(P);
+    int bands0 = 0;   // column bands of GPU 0's row block (same policy on every GPU)
     std::vector<double> objs(P, 0.0), gen_seconds(P, 0.0);
     std::vector<std::thread> workers;
     for (int p = 0; p < P; ++p) {
@@ -209,6 +210,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, 
                 const auto t1 = std::chrono::steady_clock::now();
                 eng.scale(&pp);
                 hooks[p].scaling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+                if (p == 0) bands0 = (int)eng.A.bands.size();
                 results[p] = eng.solve(&pp, &hooks[p]);
             } catch (const std::exception &e) {
                 errors[p] = e.what();
@@ -243,7 +245,7 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, 
         info->restarts = h.restarts; info->power_iters = h.power_iters; info->kernel_launches = h.kernel_launches;
         info->b_scale = h.scal[0]; info->c_scale = h.scal[1]; info->norm_b = h.scal[2]; info->norm_c = h.scal[3];
         info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
-        info->items_A = P; info->items_AT = P;
+        info->items_A = P; info->items_AT = P; info->bands_A = bands0;
     }
     return out;
 }

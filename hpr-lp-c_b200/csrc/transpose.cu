@@ -9,6 +9,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdexcept>
+#include <vector>
+
 #include "engine.h"
 #include "kernels.cuh"
 
@@ -46,6 +49,53 @@ __global__ void col_ptr_kernel(const int *sorted_cols, int nnz, int cols, int *t
     trp[c] = lo;
 }
 
+
+// ---- column bands (engine.cu, Engine::build_bands) ------------------------------------------------------------------
+// counts[b * (rows + 1) + r] = entries of row r whose column lies in band b (band = col / band_cols); one warp per row.
+constexpr int kMaxBands = 64;
+__global__ void band_count_kernel(const int *rowPtr, const int *col, int rows, int band_cols, int n_bands, int *counts) {
+    __shared__ int cnt[8][kMaxBands];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * 8 + w;
+    for (int b = lane; b < n_bands; b += 32) cnt[w][b] = 0;
+    __syncwarp();
+    if (r < rows) {
+        for (int k = rowPtr[r] + lane; k < rowPtr[r + 1]; k += 32) atomicAdd(&cnt[w][col[k] / band_cols], 1);
+    }
+    __syncwarp();
+    if (r < rows)
+        for (int b = lane; b < n_bands; b += 32) counts[(size_t)b * (rows + 1) + r] = cnt[w][b];
+}
+// Stable split: within (row, band) the entries keep their order in the row, so a banded pass adds the same products as the
+// plain pass, band by band.  One warp per row; 32 entries at a time, ranks by __match_any_sync.
+__global__ void band_fill_kernel(const int *rowPtr, const int *col, const double *val, int rows, int band_cols, int n_bands,
+                                 const int *band_rowPtr /* [n_bands][rows + 1] */, int *const *bcol, double *const *bval) {
+    __shared__ int off[8][kMaxBands];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * 8 + w;
+    for (int b = lane; b < n_bands; b += 32) off[w][b] = (r < rows) ? band_rowPtr[(size_t)b * (rows + 1) + r] : 0;
+    __syncwarp();
+    if (r >= rows) return;
+    const int p0 = rowPtr[r], p1 = rowPtr[r + 1];
+    for (int k0 = p0; k0 < p1; k0 += 32) {
+        const int k = k0 + lane;
+        const bool on = k < p1;
+        const unsigned act = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const int c = col[k];
+            const int b = c / band_cols;
+            const unsigned same = __match_any_sync(act, b);
+            const int rank = __popc(same & ((1u << lane) - 1u));
+            const int pos = off[w][b] + rank;
+            bcol[b][pos] = c;
+            bval[b][pos] = val[k];
+            __syncwarp(act);
+            if (rank == 0) off[w][b] += __popc(same);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
@@ -68,6 +118,34 @@ void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, cons
     permute_kernel<<<(nnz + T - 1) / T, T, 0, st>>>(perm, rowid, d_val, nnz, d_tcol, d_tval);
     col_ptr_kernel<<<(cols + 1 + T - 1) / T, T, 0, st>>>(keys_out, nnz, cols, d_trp);
     cudaFreeAsync(rowid, st); cudaFreeAsync(idx, st); cudaFreeAsync(keys_out, st); cudaFreeAsync(perm, st); cudaFreeAsync(tmp, st);
+}
+
+// Splits a device CSR matrix into n_bands column bands.  band_rowPtr: [n_bands][rows + 1] (device, filled here);
+// d_bcol / d_bval: device arrays of n_bands pointers to the per-band col / val arrays, which the caller allocates after
+// band_nnz (host, filled by band_count) is known.  Two steps because the sizes come from the first.
+void band_count(int rows, const int *d_rowPtr, const int *d_col, int band_cols, int n_bands, int *band_rowPtr,
+                long long *band_nnz, cudaStream_t st) {
+    if (n_bands > kMaxBands) throw std::runtime_error("too many column bands");
+    const size_t stride = (size_t)rows + 1;
+    band_count_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_rowPtr, d_col, rows, band_cols, n_bands, band_rowPtr);
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    HPR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, band_rowPtr, band_rowPtr, (int)stride, st));
+    HPR_CUDA_CHECK(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
+    std::vector<int> last(n_bands);
+    for (int b = 0; b < n_bands; ++b) {
+        int *rp = band_rowPtr + (size_t)b * stride;     // counts[rows] is 0 (zero-filled by the caller) -> rp[rows] = total
+        HPR_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rp, rp, (int)stride, st));
+        HPR_CUDA_CHECK(cudaMemcpyAsync(&last[b], rp + rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    HPR_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFreeAsync(tmp, st);
+    for (int b = 0; b < n_bands; ++b) band_nnz[b] = last[b];
+}
+void band_fill(int rows, const int *d_rowPtr, const int *d_col, const double *d_val, int band_cols, int n_bands,
+               const int *band_rowPtr, int *const *d_bcol, double *const *d_bval, cudaStream_t st) {
+    band_fill_kernel<<<(rows + 7) / 8, 256, 0, st>>>(d_rowPtr, d_col, d_val, rows, band_cols, n_bands, band_rowPtr, d_bcol, d_bval);
+    HPR_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace hpr

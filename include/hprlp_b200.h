@@ -24,6 +24,8 @@ typedef struct {
     double b_scale, c_scale, norm_b, norm_c, norm_b_org, norm_c_org;
     int lanes_A, lanes_AT;          /* per-matrix load-balance choice (lanes per row) */
     int items_A, items_AT;
+    int bands_A;                    /* column bands of A (0 = single pass; >1 when n doubles exceed the L2 budget) */
+    int reserved0;
 } hprlp_b200_info;
 
 /* HPRLP_main_solve with hooks.  power_z0 (host, length m) overrides the cuRAND start vector when
