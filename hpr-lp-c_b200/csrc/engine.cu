@@ -750,7 +750,9 @@ void Engine::scale(const HPRLP_parameters *p) {
     norm_b = nb;
     norm_c = nc;
     HPR_CUDA_CHECK(cudaGetLastError());
-    build_bands(A);   // after scaling: the bands copy the final values (no-op unless n doubles exceed the L2 budget)
+    // after scaling (the bands copy the final values); no-ops unless the gathered vector exceeds the L2 budget
+    build_bands(A);    // passes over A gather n-vectors (x_hat, x_bar, A^T q)
+    build_bands(AT);   // passes over A^T gather m-vectors (y, y_bar, q)
 }
 
 // ------------------------------------------------------------------------------------------------
