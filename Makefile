@@ -10,7 +10,7 @@ LIB := lib
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC \
            -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xcompiler -fopenmp -Iinclude
-CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Iinclude -I$(CUDA_PATH)/include
+CXXFLAGS := -O2 -std=c++17 -fPIC -fopenmp -Wall -Iinclude -I$(CUDA_PATH)/include
 LIBS := -L$(CUDA_PATH)/lib64 -lcurand -lz -lgomp -lpthread -ldl
 RPATH := -Xlinker -rpath -Xlinker $(CUDA_PATH)/lib64
 

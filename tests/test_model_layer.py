@@ -6,6 +6,7 @@ import pytest
 import scipy.sparse as sp
 
 GOLD = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+ROOT = GOLD.parent.parent
 
 
 def _rand_csr(rng, m, n, density, empty_rows=()):
@@ -182,3 +183,80 @@ def test_presolve_reduced_model_bit_exact_vs_reference(pkg, engine, reference, s
     assert (a["m"], a["n"], a["nnz"]) == (b["m"], b["n"], b["nnz"])
     for k in a:
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
+
+
+def _write_random_mps(path, seed=7, m=1500, n=12000):
+    """A few hundred KB of free-format MPS with the spellings and layouts the reader must agree on with the reference:
+    two entries per card, comments and blank lines inside sections, integer markers, duplicate cards, '+'/exponent/'D'
+    number spellings, objective entries in the middle of a column, RANGES, all bound types."""
+    rng = np.random.default_rng(seed)
+    fmt = [lambda v: f"{v:.17g}", lambda v: f"{v:+.6e}", lambda v: f"{v:.3f}", lambda v: f"{int(v)}" if v == int(v) else f"{v:.9g}",
+           lambda v: f"{v:.4f}D0"]
+    with open(path, "w") as f:
+        f.write("* generated\nNAME rnd\nROWS\n N obj\n N rim\n")
+        types = rng.choice(list("ELG"), m)
+        for i in range(m):
+            f.write(f" {types[i]}  R{i}\n")
+        f.write("COLUMNS\n")
+        for j in range(n):
+            if j % 997 == 0:
+                f.write("    MARKER  'MARKER'  'INTORG'\n" if (j // 997) % 2 == 0 else "    MARKER  'MARKER'  'INTEND'\n")
+            if j % 501 == 0:
+                f.write("* a comment inside COLUMNS\n\n")
+            k = int(rng.integers(1, 9))
+            rows = rng.choice(m, k, replace=False)
+            vals = np.round(rng.uniform(-5, 5, k), int(rng.integers(0, 6)))
+            cards = [(f"R{r}", v) for r, v in zip(rows, vals)]
+            if rng.random() < 0.5:
+                cards.insert(int(rng.integers(0, len(cards) + 1)), ("obj", float(np.round(rng.uniform(-2, 2), 3))))
+            if rng.random() < 0.05:
+                cards.append(cards[0])                      # duplicate (row, col) card
+            if rng.random() < 0.02:
+                cards.append(("rim", 1.0))
+            i = 0
+            while i < len(cards):
+                fm = fmt[int(rng.integers(0, len(fmt)))]
+                if i + 1 < len(cards) and rng.random() < 0.5:
+                    f.write(f"    C{j}  {cards[i][0]}  {fm(cards[i][1])}  {cards[i + 1][0]}  {fm(cards[i + 1][1])}\n")
+                    i += 2
+                else:
+                    f.write(f"    C{j}\t{cards[i][0]}   {fm(cards[i][1])}\n")
+                    i += 1
+        f.write("RHS\n    rhs  obj  -1.25\n")
+        for i in range(0, m, 2):
+            f.write(f"    rhs  R{i}  {rng.uniform(-3, 3):.6g}  R{min(i + 1, m - 1)}  {rng.uniform(-3, 3):.6g}\n")
+        f.write("RANGES\n")
+        for i in range(0, m, 7):
+            f.write(f"    rng  R{i}  {rng.uniform(-2, 2):.5g}\n")
+        f.write("BOUNDS\n")
+        for j in range(0, n, 3):
+            bt = ["UP", "LO", "FX", "FR", "MI", "PL", "BV"][int(rng.integers(0, 7))]
+            f.write(f" {bt} bnd  C{j}" + ("" if bt in ("FR", "MI", "PL", "BV") else f"  {rng.uniform(-4, 4):.6g}") + "\n")
+        f.write("ENDATA\n")
+
+
+@pytest.mark.parametrize("threads", [1, 7])
+def test_parallel_mps_reader_bit_exact_vs_reference(pkg, reference, tmp_path, threads):
+    """The multi-threaded COLUMNS parse (chunk boundaries fall inside column runs) against the reference's sequential
+    reader, byte for byte; run in a subprocess so OMP_NUM_THREADS takes effect."""
+    import subprocess, sys, textwrap
+    path = tmp_path / "rnd.mps"
+    _write_random_mps(path)
+    assert path.stat().st_size > 8 * 65536          # enough bytes for several parse chunks
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {str(ROOT)!r})
+        import __graft_entry__ as graft
+        pkg = graft.load_package()
+        out = []
+        for lib in (pkg.load_engine(), pkg.load_reference()):
+            mdl = lib.create_model_from_mps({str(path)!r})
+            assert mdl
+            out.append(lib.model_arrays(mdl)); lib.free_model(mdl)
+        a, b = out
+        bad = [k for k in a if not np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True)]
+        print("MISMATCH" if bad else "IDENTICAL", bad, a["m"], a["n"], a["nnz"])
+    """)
+    env = dict(**__import__("os").environ, OMP_NUM_THREADS=str(threads))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "IDENTICAL" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
