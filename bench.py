@@ -402,9 +402,12 @@ def main():
         out = run_engine_arm(args, pkg, spec, lp, rank, world, local, dist)
         e2e = None
         if not args.no_e2e:
-            e = run_e2e(pkg, pkg.load_engine(), lp, local)
+            # same protocol as the reference arm: up to 3 whole solve() calls, the best one is reported (the first call of
+            # a process also loads cuRAND's kernels for the power-iteration start vector, ~0.6 s), all are listed
+            runs = [run_e2e(pkg, pkg.load_engine(), lp, local) for _ in range(max(1, min(args.steps, 3)))]
+            e = max(runs, key=lambda r: r["value"])
             v, _ = reduce_max_sum(dist, local, 0.0, e["value"])
-            e2e = dict(e, value=_ if world > 1 else e["value"])
+            e2e = dict(e, value=_ if world > 1 else e["value"], all_runs_time_to_tol_s=[r["time_to_tol_s"] for r in runs])
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu:
             cpu = cpu_baseline(pkg, lp, iters=10 if spec["nnz"] >= 5_000_000 else 200)
