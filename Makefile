@@ -33,7 +33,7 @@ CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu 
 CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp $(SRC)/nccl_shim.cpp
 OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS)) $(PSLP_OBJS)
 
-all: $(LIB)/libhprlp.so $(LIB)/libhprlp.a $(BUILD)/solve_mps_file
+all: $(LIB)/libhprlp.so $(LIB)/libhprlp.a $(BUILD)/solve_mps_file $(BUILD)/gather_bench $(BUILD)/mps_time
 
 $(BUILD)/%.o: $(SRC)/%.cu $(SRC)/engine.h $(SRC)/kernels.cuh include/structs.h include/hprlp_b200.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
@@ -50,6 +50,13 @@ $(LIB)/libhprlp.a: $(OBJS) | $(LIB)
 
 $(BUILD)/solve_mps_file: $(SRC)/solve_mps_file.cpp $(LIB)/libhprlp.a
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -O2 -Iinclude -o $@ $< $(LIB)/libhprlp.a $(LIBS) $(RPATH)
+
+# measurement tools (not part of the product): gather-ceiling microbenchmark, MPS reader timer
+$(BUILD)/gather_bench: tools/gather_bench.cu | $(BUILD)
+	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -ccbin $(HOSTCXX) -o $@ $<
+
+$(BUILD)/mps_time: tools/mps_time.cpp $(LIB)/libhprlp.so
+	$(HOSTCXX) -O2 -std=c++17 -Iinclude -I$(CUDA_PATH)/include -o $@ $< -L$(LIB) -lhprlp -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(BUILD)/pslp/%.o: $(PSLP_DIR)/src/%.c | $(BUILD)
 	@mkdir -p $(dir $@)
