@@ -950,7 +950,12 @@ void Engine::run_normal(int count) {
 }
 
 // reference compute_residuals, src/main_iterate.cu:229-309 -- two fused passes, one D2H of 9 scalars.
+namespace { struct ResidTiming { double ms = 0.0, wait_ms = 0.0; int n = 0; } g_rt; }
 void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, RestartState *rs) {
+    static const bool timing = getenv("HPRLP_TIMING") != nullptr;
+    cudaEvent_t te0 = nullptr, te1 = nullptr;
+    double host0 = 0.0;
+    if (timing) { cudaEventCreate(&te0); cudaEventCreate(&te1); cudaEventRecord(te0, stream); host0 = now_seconds(); }
     auto fill_dual = [&](auto &o) {
         o.y_bar = y_bar; o.c = c; o.z_bar = z_bar; o.x_bar = x_bar; o.x_tmp = x_tmp; o.col_norm = col_norm;
         o.l = l; o.u = u; o.partials = d_partials;
@@ -988,8 +993,18 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         launches += 2;
     }
     allreduce(d_scal + 5, 4);   // y-side sums are partial per row block
+    if (timing) cudaEventRecord(te1, stream);
     fetch_scalars(9);
     HPR_CUDA_CHECK(cudaGetLastError());
+    if (timing) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, te0, te1);
+        g_rt.ms += ms; g_rt.wait_ms += (now_seconds() - host0) * 1e3; g_rt.n++;
+        cudaEventDestroy(te0); cudaEventDestroy(te1);
+        if (iter > 0 && iter % 100 == 0)
+            fprintf(stderr, "[hprlp timing] residual checks so far: %d, device %.2f ms (%.3f ms each), host wait incl. queued iterations %.1f ms\n",
+                    g_rt.n, g_rt.ms, g_rt.ms / g_rt.n, g_rt.wait_ms);
+    }
 
     const double obj_scale = b_scale * c_scale;
     res->primal_obj = obj_scale * h_scal[1] + obj_constant;

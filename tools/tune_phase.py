@@ -28,8 +28,8 @@ for w in wl:
             param = pkg.Parameters.default(stop_tol=0.0, use_presolve=False)
             model = lib.create_model(lp)
             h = lib.lib.hprlp_b200_engine_create(model, C.byref(param))
-            ms100 = lib.lib.hprlp_b200_engine_run(h, 100)
-            ms100 = lib.lib.hprlp_b200_engine_run(h, 100)
+            lib.lib.hprlp_b200_engine_run(h, 1000)          # past the check-every-10 regime
+            ms100 = lib.lib.hprlp_b200_engine_run(h, 500) / 5.0   # sustained (power-capped) rate, 1 check per 100 iterations
             tx = lib.lib.hprlp_b200_engine_time_phase(h, 0, 50)
             ty = lib.lib.hprlp_b200_engine_time_phase(h, 1, 50)
             lib.lib.hprlp_b200_engine_destroy(h)
