@@ -260,3 +260,44 @@ def test_parallel_mps_reader_bit_exact_vs_reference(pkg, reference, tmp_path, th
     env = dict(**__import__("os").environ, OMP_NUM_THREADS=str(threads))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert "IDENTICAL" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+_EDGE_MPS = {
+    # CRLF line endings, tab separators, blank and comment lines between cards
+    "crlf_tabs": "NAME\tt\r\nROWS\r\n N\tobj\r\n L\tr1\r\n G\tr2\r\n\r\n* comment\r\nCOLUMNS\r\n\tx\tobj\t1\tr1\t2\r\n\tx\tr2\t3\r\n\ty\tr1\t-1.5\r\n"
+                 "RHS\r\n\trhs\tr1\t4\tr2\t1\r\nBOUNDS\r\n UP\tb\tx\t10\r\nENDATA\r\n",
+    # no ENDATA, no trailing newline, RHS/RANGES/BOUNDS absent
+    "no_endata": "NAME t\nROWS\n N obj\n E r1\nCOLUMNS\n x obj 1 r1 1\n y r1 2",
+    # unknown row in COLUMNS / RHS / RANGES, unknown column in BOUNDS, short lines, unknown bound type, rim RHS/RANGES/BOUNDS sets
+    "unknowns": "NAME t\nROWS\n N obj\n L r1\n G r2\nCOLUMNS\n x obj 1 nosuch 5\n x r1 1\n y r2 2 r1 1\n z\n z r1\n"
+                "RHS\n rhs r1 3 nosuch 1\n rhs2 r2 9\n rhs\nRANGES\n rng nosuch 1\n rng r1 2\n rng2 r2 5\n"
+                "BOUNDS\n UP b nosuch 1\n XX b x 1\n LO b y -2\n UP b2 y 5\n UP b\nENDATA\n",
+    # duplicate row name (re-bound), N row after constraints (rim), second objective entry overriding the first
+    "rebinding": "NAME t\nROWS\n N obj\n L r1\n G r1\n E r2\n N late\nCOLUMNS\n x obj 1 r1 1\n x obj 7\n x late 3\n y r2 1 r1 4\nRHS\n rhs r1 2 r2 1\nENDATA\n",
+    # number spellings: sign, exponent, leading dot, Fortran D (atof stops at D), inf, trailing junk
+    "numbers": "NAME t\nROWS\n N obj\n L r1\n G r2\n E r3\nCOLUMNS\n a obj +1.5 r1 1e0\n a r2 .5 r3 -2.5E-1\n b r1 1.0D3 r2 3abc\n b r3 1e400\n c r1 -0 r2 0x10\n"
+               "RHS\n rhs r1 +4 r2 -1e-3\n rhs r3 1e30\nBOUNDS\n UP b a 1e30\n LO b b -inf\n UP b c Infinity\nENDATA\n",
+    # negative upper bound without a lower bound, MI then UP, FX, BV, PL, integer markers with default [0,1]
+    "bounds": "NAME t\nROWS\n N obj\n L r1\nCOLUMNS\n a r1 1 obj 1\n MARKER 'MARKER' 'INTORG'\n b r1 1\n c r1 1\n MARKER 'MARKER' 'INTEND'\n d r1 1\n e r1 1\n f r1 1\n"
+              "RHS\n rhs r1 5\nBOUNDS\n UP bnd a -3\n MI bnd d\n UP bnd d 2\n FX bnd e 1.5\n BV bnd f\n PL bnd c\n LI bnd b 0\n UI bnd b 7\nENDATA\n",
+    # RANGES on E rows with both signs, on L and G rows, on the objective (error), OBJSENSE MAX (ignored)
+    "ranges": "NAME t\nOBJSENSE\n MAX\nROWS\n N obj\n E e1\n E e2\n L l1\n G g1\nCOLUMNS\n x obj 1 e1 1\n x e2 1 l1 1\n x g1 1\n"
+              "RHS\n rhs e1 1 e2 1\n rhs l1 1 g1 1\nRANGES\n rng e1 2 e2 -2\n rng l1 -3 g1 -4\n rng obj 1\nENDATA\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(_EDGE_MPS))
+def test_mps_edge_cases_bit_exact_vs_reference(engine, reference, tmp_path, name):
+    """Reader corner cases (tokenising, error paths that must not change the model, number spellings, bound and range
+    rules): the arrays must equal the reference reader's byte for byte."""
+    path = tmp_path / f"{name}.mps"
+    path.write_bytes(_EDGE_MPS[name].encode())
+    mine = engine.create_model_from_mps(path)
+    ref = reference.create_model_from_mps(path)
+    assert bool(mine) == bool(ref)
+    if not mine:
+        return
+    a, b = engine.model_arrays(mine), reference.model_arrays(ref)
+    engine.free_model(mine); reference.free_model(ref)
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), (name, k, a[k], b[k])
