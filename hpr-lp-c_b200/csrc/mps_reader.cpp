@@ -16,6 +16,10 @@
 // short sequential pass numbers the columns in order of first appearance (and tracks the integer markers), a
 // second parallel sweep converts the entries; COO -> CSR is a counting sort by row + per-row stable sorts, in
 // parallel.  The small sections (ROWS, RHS, RANGES, BOUNDS) stay sequential.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -360,40 +364,51 @@ const char *next_header(const char *p, const char *end) {
     return end;
 }
 
-bool read_whole(const char *path, std::vector<char> &buf) {
-    // plain files: one fread of the whole file; gzip files (magic 1f 8b): inflate through zlib
-    FILE *fp = std::fopen(path, "rb");
-    if (!fp) return false;
+// The whole file as one read-only byte range: plain files are mapped (no copy), gzip files (magic 1f 8b) are inflated
+// through zlib into a heap buffer.
+struct FileBytes {
+    const char *data = nullptr;
+    size_t size = 0;
+    void *map = nullptr;
+    size_t map_len = 0;
+    std::vector<char> heap;
+    ~FileBytes() { if (map) munmap(map, map_len); }
+};
+
+bool read_whole(const char *path, FileBytes &fb) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
     unsigned char magic[2] = {0, 0};
-    const size_t got2 = std::fread(magic, 1, 2, fp);
+    const ssize_t got2 = pread(fd, magic, 2, 0);
     const bool gz = got2 == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-    if (!gz) {
-        std::fseek(fp, 0, SEEK_END);
-        const long size = std::ftell(fp);
-        if (size >= 0) {
-            std::fseek(fp, 0, SEEK_SET);
-            buf.resize((size_t)size);
-            const size_t got = size > 0 ? std::fread(buf.data(), 1, (size_t)size, fp) : 0;
-            std::fclose(fp);
-            buf.resize(got);
+    struct stat st;
+    if (!gz && fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+        if (st.st_size == 0) { close(fd); return true; }
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (m != MAP_FAILED) {
+            close(fd);
+            madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+            fb.map = m; fb.map_len = (size_t)st.st_size;
+            fb.data = static_cast<const char *>(m); fb.size = (size_t)st.st_size;
             return true;
         }
     }
-    std::fclose(fp);
-    gzFile f = gzopen(path, "rb");   // gzip (or a non-seekable plain stream: zlib reads those transparently)
+    close(fd);
+    gzFile f = gzopen(path, "rb");   // gzip (or a non-regular plain stream: zlib reads those transparently)
     if (!f) return false;
     gzbuffer(f, 1 << 20);
     size_t cap = (size_t)1 << 24, len = 0;
-    buf.resize(cap);
+    fb.heap.resize(cap);
     for (;;) {
-        if (len == cap) { cap *= 2; buf.resize(cap); }
+        if (len == cap) { cap *= 2; fb.heap.resize(cap); }
         const int want = (int)std::min<size_t>(cap - len, (size_t)1 << 30);
-        const int got = gzread(f, buf.data() + len, (unsigned)want);
+        const int got = gzread(f, fb.heap.data() + len, (unsigned)want);
         if (got <= 0) break;
         len += (size_t)got;
     }
     gzclose(f);
-    buf.resize(len);
+    fb.heap.resize(len);
+    fb.data = fb.heap.data(); fb.size = len;
     return true;
 }
 
@@ -402,14 +417,14 @@ bool read_whole(const char *path, std::vector<char> &buf) {
 bool build_model_from_mps(const char *path, LP_info_cpu *lp) {
     std::printf("Start reading file....\n");
     const auto t0 = std::chrono::steady_clock::now();   // wall clock (the parse is multi-threaded; clock() would add the threads up)
-    std::vector<char> buf;
+    FileBytes buf;
     if (!read_whole(path, buf)) {
         std::cerr << "Error: Cannot open file " << path << "\n";
         std::cerr << "Error: Failed to read MPS file\n";
         return false;
     }
-    if (g_timing) std::fprintf(stderr, "[hprlp timing] file read %.3f s (%.1f MB)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), buf.size() / 1e6);
-    const char *p = buf.data(), *end = buf.data() + buf.size();
+    if (g_timing) std::fprintf(stderr, "[hprlp timing] file read %.3f s (%.1f MB)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), buf.size / 1e6);
+    const char *p = buf.data, *end = buf.data + buf.size;
     MpsData d;
     Section sec = S_NONE;
     bool integer_section = false, seen_rows = false, seen_cols = false, endata = false;
@@ -525,42 +540,69 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp) {
     }
     std::printf("File reading time: %.4f seconds\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 
-    // COO -> CSR: sort by (row, col), sum duplicates.  Counting sort by row (stable), then every row sorted by column
-    // (stable: duplicates keep file order), rows in parallel.
+    // COO -> CSR: sort by (row, col), sum duplicates.  Stable counting sort by row, by all threads (thread t scatters the
+    // t-th slice of the file-ordered entries behind the slices before it), then every row stable-sorted by column when it
+    // is not already in order; rows in parallel.
     const size_t ne = d.entries.size();
     std::vector<Coo> sorted(ne);
+    std::vector<size_t> start((size_t)m + 1, 0);
+    size_t n_dup = 0;
     {
-        std::vector<size_t> start((size_t)m + 1, 0);
-        for (size_t k = 0; k < ne; ++k) start[(size_t)d.entries[k].row + 1]++;
-        for (int i = 0; i < m; ++i) start[i + 1] += start[i];
-        std::vector<size_t> cursor(start.begin(), start.end() - 1);
-        for (size_t k = 0; k < ne; ++k) sorted[cursor[d.entries[k].row]++] = d.entries[k];
+        const int T = (int)std::max<long long>(1, std::min<long long>(host_threads(), (long long)(ne >> 16) + 1));
+        std::vector<std::vector<unsigned>> cnt(T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            cnt[t].assign((size_t)m, 0u);
+            const size_t lo = ne * (size_t)t / T, hi = ne * (size_t)(t + 1) / T;
+            for (size_t k = lo; k < hi; ++k) cnt[t][d.entries[k].row]++;
+        }
+        for (int i = 0; i < m; ++i) {   // start[i]: first slot of row i; cnt[t][i] becomes thread t's first slot in row i
+            size_t run = start[i];
+            for (int t = 0; t < T; ++t) { const unsigned c = cnt[t][i]; cnt[t][i] = (unsigned)(run - start[i]); run += c; }
+            start[i + 1] = run;
+        }
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            const size_t lo = ne * (size_t)t / T, hi = ne * (size_t)(t + 1) / T;
+            for (size_t k = lo; k < hi; ++k) {
+                const int r = d.entries[k].row;
+                sorted[start[r] + cnt[t][r]++] = d.entries[k];
+            }
+        }
         std::vector<Coo>().swap(d.entries);
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_dup)
         for (int i = 0; i < m; ++i) {
             Coo *rb = sorted.data() + start[i], *re = sorted.data() + start[i + 1];
             bool in_order = true;
             for (Coo *q = rb + 1; q < re; ++q)
                 if (q->col < q[-1].col) { in_order = false; break; }
             if (!in_order) std::stable_sort(rb, re, [](const Coo &a, const Coo &b) { return a.col < b.col; });
+            for (Coo *q = rb + 1; q < re; ++q)
+                if (q->col == q[-1].col) ++n_dup;
         }
     }
-    if (g_timing) std::fprintf(stderr, "[hprlp timing] sorted at %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    if (g_timing) std::fprintf(stderr, "[hprlp timing] sorted at %.3f s (%zu duplicate cards)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), n_dup);
     std::vector<int> cols; std::vector<double> vals;
-    cols.reserve(ne); vals.reserve(ne);
-    for (size_t k = 0; k < ne; ++k) {
-        if (k > 0 && sorted[k].row == sorted[k - 1].row && sorted[k].col == sorted[k - 1].col) {
-            vals.back() += sorted[k].val;
-        } else {
-            cols.push_back(sorted[k].col); vals.push_back(sorted[k].val);
-        }
-    }
-    // Row pointers: the reference derives them from the first unique_nnz entries of the SORTED,
-    // NOT-YET-DEDUPLICATED list (src/mps_reader.cpp:1336-1355).  Without duplicate (row,col) cards this
-    // is the ordinary CSR row pointer; with duplicates it mis-assigns row boundaries.  Mirrored exactly
-    // so that the model arrays stay bit-identical to the reference on every input (DESIGN.md quirk list).
     std::vector<int> rowptr((size_t)m + 1, 0);
-    {
+    if (n_dup == 0) {
+        // no duplicate (row, col) card: the sorted list IS the CSR matrix
+        cols.resize(ne); vals.resize(ne);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < (long long)ne; ++k) { cols[k] = sorted[k].col; vals[k] = sorted[k].val; }
+        for (int i = 0; i <= m; ++i) rowptr[i] = (int)start[i];
+    } else {
+        cols.reserve(ne); vals.reserve(ne);
+        for (size_t k = 0; k < ne; ++k) {
+            if (k > 0 && sorted[k].row == sorted[k - 1].row && sorted[k].col == sorted[k - 1].col) {
+                vals.back() += sorted[k].val;
+            } else {
+                cols.push_back(sorted[k].col); vals.push_back(sorted[k].val);
+            }
+        }
+        // Row pointers: the reference derives them from the first unique_nnz entries of the SORTED,
+        // NOT-YET-DEDUPLICATED list (src/mps_reader.cpp:1336-1355).  Without duplicate (row,col) cards this
+        // is the ordinary CSR row pointer (the branch above); with duplicates it mis-assigns row boundaries.  Mirrored
+        // exactly so that the model arrays stay bit-identical to the reference on every input (DESIGN.md quirk list).
         int row = 0;
         for (size_t i = 0; i < vals.size(); ++i) {
             const int entry_row = sorted[i].row;

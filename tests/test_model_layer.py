@@ -185,7 +185,7 @@ def test_presolve_reduced_model_bit_exact_vs_reference(pkg, engine, reference, s
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
 
 
-def _write_random_mps(path, seed=7, m=1500, n=12000):
+def _write_random_mps(path, seed=7, m=1500, n=12000, dups=True):
     """A few hundred KB of free-format MPS with the spellings and layouts the reader must agree on with the reference:
     two entries per card, comments and blank lines inside sections, integer markers, duplicate cards, '+'/exponent/'D'
     number spellings, objective entries in the middle of a column, RANGES, all bound types."""
@@ -209,7 +209,7 @@ def _write_random_mps(path, seed=7, m=1500, n=12000):
             cards = [(f"R{r}", v) for r, v in zip(rows, vals)]
             if rng.random() < 0.5:
                 cards.insert(int(rng.integers(0, len(cards) + 1)), ("obj", float(np.round(rng.uniform(-2, 2), 3))))
-            if rng.random() < 0.05:
+            if dups and rng.random() < 0.05:
                 cards.append(cards[0])                      # duplicate (row, col) card
             if rng.random() < 0.02:
                 cards.append(("rim", 1.0))
@@ -235,13 +235,13 @@ def _write_random_mps(path, seed=7, m=1500, n=12000):
         f.write("ENDATA\n")
 
 
-@pytest.mark.parametrize("threads", [1, 7])
-def test_parallel_mps_reader_bit_exact_vs_reference(pkg, reference, tmp_path, threads):
+@pytest.mark.parametrize("threads,dups", [(1, True), (7, True), (5, False)])
+def test_parallel_mps_reader_bit_exact_vs_reference(pkg, reference, tmp_path, threads, dups):
     """The multi-threaded COLUMNS parse (chunk boundaries fall inside column runs) against the reference's sequential
     reader, byte for byte; run in a subprocess so OMP_NUM_THREADS takes effect."""
     import subprocess, sys, textwrap
     path = tmp_path / "rnd.mps"
-    _write_random_mps(path)
+    _write_random_mps(path, dups=dups)      # dups=False: the direct sorted-list-is-CSR path of the reader
     assert path.stat().st_size > 8 * 65536          # enough bytes for several parse chunks
     code = textwrap.dedent(f"""
         import sys, numpy as np
