@@ -251,7 +251,7 @@ static inline int vec_grid(int len) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-// per-CTA partial blocks written by one streamed pass: main-kernel CTAs + fix-up CTAs
+// per-CTA partial blocks written by one streamed pass (a banded pass reduces in its last band only)
 static int part_blocks(const DevCsr &M) { return M.bands.empty() ? M.n_items : M.bands.back().n_items; }
 
 static CsrView<int> view_of(const DevCsr &M) {

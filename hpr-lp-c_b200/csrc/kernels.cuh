@@ -4,10 +4,10 @@
 // fused HPR phases, the KKT residual passes, power iteration, Ruiz/Pock-Chambolle/Curtis-Reid
 // row statistics).  It is an nnz-balanced ("merge-style") CSR-stream kernel at WARP granularity:
 //
-//   item  = a fixed chunk of kWarpChunk (512) consecutive nonzeros owned by ONE WARP, so the work
+//   item  = a fixed chunk of kWarpChunk (256) consecutive nonzeros owned by ONE WARP, so the work
 //           per warp is identical whatever the row-length distribution is (power-law rows
 //           included; no row-id lists, no short/long buckets) and warps never wait on each other:
-//           there is no CTA barrier on the path, every warp of an SM is at a different point of
+//           there is no CTA barrier on the path (one at kernel entry only), every warp of an SM is at a different point of
 //           its item, which is what hides the HBM/L2 latency of the gathers (r1 v1 used CTA-wide
 //           items + __syncthreads and was latency-bound: profiles/r1_v1_ncu_full_c2_details.txt).
 //   phase 1  the warp streams its nonzeros with 128-bit/64-bit coalesced loads (double2 values,
