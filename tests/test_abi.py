@@ -106,3 +106,23 @@ def test_error_behaviour_without_gpu(engine, pkg):
     engine.lib.free_batched_results(C.byref(br))
     assert not br.status
     del bad
+
+
+def test_cli_argument_handling_matches_reference_cli():
+    """build/solve_mps_file: the reference CLI's diagnostics and exit codes for the paths that need no GPU
+    (reference src/solve_mps_file.cpp:34-122)."""
+    import subprocess
+    exe = str(ROOT / "build" / "solve_mps_file")
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, timeout=60)
+    r = run("--help")
+    assert r.returncode == 0 and "Usage:" in r.stdout and "--presolve <true/false>" in r.stdout
+    r = run()
+    assert r.returncode == 1 and "Error: Input file is required. Use -i or --input option." in r.stderr
+    r = run("-i")
+    assert r.returncode == 1 and "Missing value for option: -i" in r.stderr
+    r = run("--tol")
+    assert r.returncode == 1 and "Missing value for option: --tol" in r.stderr
+    r = run("--bogus", "1")
+    assert r.returncode == 1 and "Unknown option: --bogus" in r.stderr
+    r = run("-i", "/no/such/file.mps")
+    assert r.returncode == 1 and "Input file does not exist: /no/such/file.mps" in r.stderr
