@@ -126,3 +126,26 @@ def test_cli_argument_handling_matches_reference_cli():
     assert r.returncode == 1 and "Unknown option: --bogus" in r.stderr
     r = run("-i", "/no/such/file.mps")
     assert r.returncode == 1 and "Input file does not exist: /no/such/file.mps" in r.stderr
+
+
+def test_error_paths_same_as_reference_build(engine, reference, pkg):
+    """The host-only error paths side by side with the reference's own build: same NULL / non-NULL results, same status
+    strings, same batched error shape."""
+    outcomes = []
+    for lib in (engine, reference):
+        L = lib.lib
+        o = []
+        o.append(bool(L.create_model_from_arrays(0, 2, 4, None, None, None, None, None, None, None, None, False)))
+        o.append(bool(L.create_model_from_arrays(2, 2, 4, None, None, None, None, None, None, None, None, False)))
+        o.append(bool(L.create_model_from_arrays(2, 0, 4, None, None, None, None, None, None, None, None, True)))
+        o.append(bool(L.create_model_from_mps(None)))
+        o.append(bool(L.create_model_from_mps(b"/nonexistent/file.mps")))
+        r = L.solve(None, None)
+        o.append((r.status, bool(r.x), bool(r.y), bool(r.z), r.iter))
+        for B in (3, 0, -2):
+            br = L.solve_batched(None, B, None, None, None, None, None, None, None)
+            o.append((br.batch_size, C.string_at(br.status, 5) if br.status else None, bool(br.x), bool(br.iter)))
+            L.free_batched_results(C.byref(br))
+            o.append(bool(br.status))
+        outcomes.append(o)
+    assert outcomes[0] == outcomes[1], outcomes
