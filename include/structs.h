@@ -14,8 +14,19 @@
  * declares its internal GPU workspace (cuSPARSE/cuBLAS handles) in this header; that is
  * not part of the ABI and lives in hpr-lp-c_b200/csrc/engine.h here, so consumers of this
  * header need neither cuBLAS nor cuSPARSE headers.
+ *
+ * Source compatibility: consumers of the reference header also get <cmath> (INFINITY), <limits>, <string> and
+ * <vector> through it (the reference pulls them in next to cublas_v2.h); its own examples rely on that
+ * (examples/cpp/example_direct_lp.cpp uses INFINITY with no include of its own), so they are included here too.
  */
+#include <math.h>
 #include <stdint.h>
+#ifdef __cplusplus
+#include <cmath>
+#include <limits>
+#include <string>
+#include <vector>
+#endif
 
 #define HPRLP_FLOAT double
 

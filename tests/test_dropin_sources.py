@@ -1,0 +1,69 @@
+"""CPU: the reference's own consumers build UNCHANGED against include/ + lib/ (drop-in boundary).
+The sources are compiled from where they lie under /root/reference (nothing is copied into the repo); the GPU box has no
+reference tree, so these tests run in the build container only."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("HPRLP_REFERENCE_DIR", "/root/reference"))
+NVCC = "/usr/local/cuda/bin/nvcc"
+
+pytestmark = pytest.mark.skipif(not (REF / "examples").is_dir(), reason="reference tree not present")
+
+
+def _sh(cmd, **kw):
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+    assert r.returncode == 0, (" ".join(map(str, cmd)), r.stdout[-1500:], r.stderr[-3000:])
+    return r
+
+
+@pytest.mark.parametrize("src", ["example_direct_lp.c", "example_mps_file.c", "example_batched_lp.c"])
+def test_reference_c_examples_compile_and_link(tmp_path, src):
+    """examples/c/Makefile:45-54: nvcc -x cu, -lhprlp -lcublas -lcusolver -lcusparse -lstdc++."""
+    _sh([NVCC, "-w", "-O2", "-arch=sm_100", "-x", "cu", f"-I{ROOT / 'include'}", "-I/usr/local/cuda/include",
+         str(REF / "examples" / "c" / src), "-o", str(tmp_path / "a.out"), f"-L{ROOT / 'lib'}", "-L/usr/local/cuda/lib64",
+         "-lhprlp", "-lcublas", "-lcusolver", "-lcusparse", "-lstdc++", "-Xlinker", "-rpath", "-Xlinker", str(ROOT / "lib")])
+
+
+@pytest.mark.parametrize("src", ["example_direct_lp.cpp", "example_mps_file.cpp"])
+def test_reference_cpp_examples_compile_and_link(tmp_path, src):
+    """examples/cpp/Makefile: nvcc --std=c++17, -lhprlp -lcublas -lcusolver -lcusparse (example_direct_lp.cpp takes INFINITY
+    from the library header)."""
+    _sh([NVCC, "-w", "-O2", "--std=c++17", "-arch=sm_100", f"-I{ROOT / 'include'}", "-I/usr/local/cuda/include",
+         str(REF / "examples" / "cpp" / src), "-o", str(tmp_path / "a.out"), f"-L{ROOT / 'lib'}", "-L/usr/local/cuda/lib64",
+         "-lhprlp", "-lcublas", "-lcusolver", "-lcusparse", "-Xlinker", "-rpath", "-Xlinker", str(ROOT / "lib")])
+
+
+def test_reference_pybind_module_builds_and_runs_host_calls(tmp_path):
+    """bindings/python/src/hprlp_pybind.cpp (includes HPRLP.h, structs.h, mps_reader.h) against this library: build,
+    import, and drive the host-only calls (MPS parse, model from arrays, parameter struct)."""
+    pybind11 = pytest.importorskip("pybind11")
+    import sysconfig
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    out = tmp_path / f"_hprlp_core{ext}"
+    _sh(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}",
+         f"-I{ROOT / 'include'}", "-I/usr/local/cuda/include", str(REF / "bindings" / "python" / "src" / "hprlp_pybind.cpp"),
+         f"-L{ROOT / 'lib'}", "-lhprlp", f"-Wl,-rpath,{ROOT / 'lib'}", "-o", str(out)])
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {str(tmp_path)!r})
+        import _hprlp_core as core
+        p = core.Parameters()
+        assert (p.max_iter, p.stop_tol, p.time_limit, p.check_iter, p.use_presolve) == (2**31 - 1, 1e-4, 3600.0, 150, True)
+        m = core.create_model_from_mps({str(ROOT / 'tests' / 'golden' / 'model.mps')!r})
+        assert m.is_valid() and (m.m, m.n) == (2, 2)
+        core.free_model(m)
+        rp = np.array([0, 2, 4], np.int32); ci = np.array([0, 1, 0, 1], np.int32); v = np.array([1., 2., 3., 1.])
+        m2 = core.create_model_from_arrays(2, 2, 4, rp, ci, v, np.array([-np.inf, -np.inf]), np.array([10., 12.]),
+                                           np.zeros(2), np.full(2, np.inf), np.array([-3., -5.]), False)
+        assert m2.is_valid() and (m2.m, m2.n) == (2, 2)
+        core.free_model(m2)
+        print("BINDING_OK")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "BINDING_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
