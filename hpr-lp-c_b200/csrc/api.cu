@@ -266,11 +266,11 @@ LP_info_cpu *create_model_from_arrays(int m, int n, int nnz, const int *rowPtr, 
     model->A->value = static_cast<double *>(std::malloc(sizeof(double) * (size_t)nnz));
     if (is_csc) {
         // CSC(A) is CSR(A^T): transposing it (stable counting sort) yields CSR(A) (src/HPRLP.cu:354-396)
-        hpr::csr_transpose_host(n, m, nnz, rowPtr, colIndex, values, model->A->rowPtr, model->A->colIndex, model->A->value);
+        hpr::csr_transpose_host_mt(n, m, nnz, rowPtr, colIndex, values, model->A->rowPtr, model->A->colIndex, model->A->value);
     } else {
         std::memcpy(model->A->rowPtr, rowPtr, sizeof(int) * ((size_t)m + 1));
-        std::memcpy(model->A->colIndex, colIndex, sizeof(int) * (size_t)nnz);
-        std::memcpy(model->A->value, values, sizeof(double) * (size_t)nnz);
+        hpr::copy_mt(model->A->colIndex, colIndex, sizeof(int) * (size_t)nnz);
+        hpr::copy_mt(model->A->value, values, sizeof(double) * (size_t)nnz);
     }
     std::printf("problem information: nRow = %d, nCol = %d, nnz A = %d\n\n", m, n, nnz);
     auto dup = [](const double *src, int len) {

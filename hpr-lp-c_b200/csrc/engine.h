@@ -181,6 +181,11 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp);
 void csr_transpose_host(int rows, int cols, int nnz, const int *rp, const int *ci, const double *v,
                         int *trp, int *tci, double *tv);
 
+// host_utils.cpp
+void copy_mt(void *dst, const void *src, size_t bytes);
+void csr_transpose_host_mt(int rows, int cols, int nnz, const int *rp, const int *ci, const double *v, int *trp, int *tci,
+                           double *tv);
+
 void band_count(int rows, const int *d_rowPtr, const int *d_col, int band_cols, int n_bands, int *band_rowPtr,
                 long long *band_nnz, cudaStream_t st);
 void band_fill(int rows, const int *d_rowPtr, const int *d_col, const double *d_val, int band_cols, int n_bands,

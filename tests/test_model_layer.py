@@ -301,3 +301,20 @@ def test_mps_edge_cases_bit_exact_vs_reference(engine, reference, tmp_path, name
     engine.free_model(mine); reference.free_model(ref)
     for k in a:
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), (name, k, a[k], b[k])
+
+
+def test_csc_input_multithreaded_conversion_bit_exact(engine, reference, pkg):
+    """CSC -> CSR of create_model_from_arrays(is_csc=true) on a matrix large enough for the multi-threaded conversion
+    (csrc/host_utils.cpp): same arrays as the reference's single-threaded counting sort, and as the CSR input path."""
+    lp = pkg.synth_lp("powerlaw", 40000, 90000, 3_000_000)
+    A = sp.csr_matrix((lp["values"], lp["colIndex"], lp["rowPtr"]), shape=(lp["m"], lp["n"]))
+    Ac = A.tocsc(); Ac.sort_indices()
+    lpc = dict(lp, rowPtr=Ac.indptr.astype(np.int32), colIndex=Ac.indices.astype(np.int32), values=Ac.data)
+    got = {}
+    for tag, lib, d, csc in (("ours_csc", engine, lpc, True), ("ref_csc", reference, lpc, True), ("ours_csr", engine, lp, False)):
+        mdl = lib.create_model(d, is_csc=csc)
+        got[tag] = lib.model_arrays(mdl)
+        lib.free_model(mdl)
+    for other in ("ref_csc", "ours_csr"):
+        for k in got["ours_csc"]:
+            assert np.array_equal(np.asarray(got["ours_csc"][k]), np.asarray(got[other][k])), (other, k)
