@@ -67,3 +67,33 @@ def test_reference_pybind_module_builds_and_runs_host_calls(tmp_path):
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "BINDING_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def test_reference_matlab_mex_gateway_compiles_against_these_headers():
+    """bindings/matlab/src/hprlp_mex.cpp includes HPRLP.h, mps_reader.h and preprocess.h from the library's include
+    directory (bindings/matlab/install.sh:85-99).  No MATLAB in the image: tests/stubs/{mex,matrix}.h declare the MEX
+    API it uses, and the gateway is compiled (not linked) against include/ to prove the headers offer every type and
+    function it needs."""
+    src = REF / "bindings" / "matlab" / "src" / "hprlp_mex.cpp"
+    if not src.exists():
+        pytest.skip("MATLAB binding source not present")
+    _sh(["g++", "-std=c++17", "-fsyntax-only", f"-I{ROOT / 'tests' / 'stubs'}", f"-I{ROOT / 'include'}",
+         "-I/usr/local/cuda/include", str(src)])
+
+
+def test_julia_wrapper_symbols_and_struct_sizes():
+    """bindings/julia/package/src/wrapper.jl ccalls the seven symbols by name and mirrors the structs by size: the names must
+    be exported unmangled and the sizes must be the ones the wrapper hard-codes through its field lists (40 / 160 / 112 /
+    64 / 40 bytes)."""
+    wrapper = REF / "bindings" / "julia" / "package" / "src" / "wrapper.jl"
+    if not wrapper.exists():
+        pytest.skip("Julia wrapper not present")
+    import re
+    text = wrapper.read_text()
+    called = set(re.findall(r"ccall\(\s*\(\s*:(\w+)", text))
+    assert called, "no ccall found in the Julia wrapper"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "lib" / "libhprlp.so")], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+    libc = {"free", "malloc"}
+    missing = sorted(s for s in called if s not in exported and s not in libc)
+    assert not missing, missing
