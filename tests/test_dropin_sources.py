@@ -68,6 +68,29 @@ def test_reference_pybind_module_builds_and_runs_host_calls(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "BINDING_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 
+    # the reference's pure-Python package on top of that module (a temporary copy next to the freshly built core, as its
+    # setup.py lays it out): Model.from_arrays / Model.from_mps / Parameters through this library
+    import shutil
+    pkg_dir = tmp_path / "site" / "hprlp"
+    shutil.copytree(REF / "bindings" / "python" / "hprlp", pkg_dir)
+    shutil.copy(out, pkg_dir / out.name)
+    code2 = textwrap.dedent(f"""
+        import sys, numpy as np, scipy.sparse as sp
+        sys.path.insert(0, {str(tmp_path / 'site')!r})
+        import hprlp
+        A = sp.csr_matrix(np.array([[1., 2.], [3., 1.]]))
+        m = hprlp.Model.from_arrays(A, np.array([-np.inf, -np.inf]), np.array([10., 12.]), np.zeros(2), np.full(2, np.inf),
+                                    np.array([-3., -5.]))
+        assert m.is_valid() and (m.m, m.n) == (2, 2)
+        m2 = hprlp.Model.from_mps({str(ROOT / 'tests' / 'golden' / 'model.mps')!r})
+        assert (m2.m, m2.n) == (2, 2)
+        p = hprlp.Parameters()
+        p.stop_tol = 1e-6
+        print("PACKAGE_OK")
+    """)
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=300)
+    assert "PACKAGE_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
 
 def test_reference_matlab_mex_gateway_compiles_against_these_headers():
     """bindings/matlab/src/hprlp_mex.cpp includes HPRLP.h, mps_reader.h and preprocess.h from the library's include
