@@ -387,9 +387,10 @@ def main():
                        how="(k2-k1) iterations / (results.time[max_iter=k2] - results.time[max_iter=k1]), k1=1000, k2-k1=2000 (nnz>=5e7) or 20000", times=rate_ts), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                    data="synthetic", config=dict(workload=spec["name"], m=lp["m"], n=lp["n"], nnz=int(lp["values"].shape[0]),
                                                  note="value = steady-state loop rate from two max_iter runs; e2e = one solve() call to KKT<1e-4 through the reference's own C API"),
-                   cpu_baseline=dict(value=best["value"], unit="HPR iterations/s", cores=0, kind="reference",
-                                     sample="the reference has no CPU path (BASELINE.json): its own CUDA build "
-                                            "(oracle/_ref/libhprlp_ref.so, autotuned fused/cuSPARSE backend) on the same B200, whole solve() call"),
+                   cpu_baseline=dict(value=rate, unit="HPR iterations/s", cores=1, kind="reference",
+                                     sample="the reference has no CPU path (BASELINE.json): this arm is its own CUDA build "
+                                            "(oracle/_ref/libhprlp_ref.so, autotuned fused/cuSPARSE backend) on the same B200, driven by one "
+                                            "host thread; value = the line's steady-state loop rate, e2e = whole solve() calls to KKT<1e-4"),
                    e2e=dict(best, h2d_bytes_per_step=0, d2h_bytes_per_step=0), clocks=clk.summary(), all_runs=runs)
         print(json.dumps(out))
         return 0
