@@ -225,7 +225,8 @@ def run_engine_arm(args, pkg, spec, lp, rank, world, local, dist):
                         source="profiles/r1_gather_ceiling.json SPMV_TEX, gathered vector of %d doubles" % best["V"])
         except Exception:
             port = None
-    roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, request_port=port,
+    roof = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, frac_of_nominal_8000_gbs=achieved / 8000.0,
+                traffic=traffic, request_port=port,
                 peak_source=peak_src, kernel=f"csr_stream_kernel<{'YPhaseOp' if dom == 'y' else 'XPhaseOp'}<false>> ({dom}-phase)",
                 algorithmic_bytes_per_launch=ab[dom], launch_ms=dur_ms,
                 x_phase=dict(ms=tx, gbs=ab["x"] / (tx * 1e-3) / 1e9), y_phase=dict(ms=ty, gbs=ab["y"] / (ty * 1e-3) / 1e9),
