@@ -29,13 +29,13 @@ $(warning PSLP sources not found; reusing prebuilt objects in $(BUILD)/pslp)
 endif
 endif
 
-CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu $(SRC)/partitioned.cu $(SRC)/synth_device.cu
+CU_SRCS := $(SRC)/engine.cu $(SRC)/api.cu $(SRC)/batched.cu $(SRC)/transpose.cu $(SRC)/partitioned.cu $(SRC)/synth_device.cu $(SRC)/collective.cu
 CPP_SRCS := $(SRC)/mps_reader.cpp $(SRC)/presolve.cpp $(SRC)/nccl_shim.cpp $(SRC)/host_utils.cpp
 OBJS := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS)) $(PSLP_OBJS)
 
 all: $(LIB)/libhprlp.so $(LIB)/libhprlp.a $(BUILD)/solve_mps_file $(BUILD)/gather_bench $(BUILD)/mps_time
 
-$(BUILD)/%.o: $(SRC)/%.cu $(SRC)/engine.h $(SRC)/kernels.cuh include/structs.h include/hprlp_b200.h | $(BUILD)
+$(BUILD)/%.o: $(SRC)/%.cu $(SRC)/engine.h $(SRC)/kernels.cuh $(SRC)/collective.h $(SRC)/rank_group.h $(SRC)/abi_guard.h include/structs.h include/hprlp_b200.h | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
 $(BUILD)/%.o: $(SRC)/%.cpp $(SRC)/engine.h include/structs.h | $(BUILD)

@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- HPR iterations/s of the B200-native engine on BASELINE.json's configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|small|c3band]
 
-One "step" = ITERS_PER_STEP (100) consecutive HPR iterations of the full driver (fused x/y phase
-kernels, the check iterations and residual passes the reference's schedule puts among them, restarts
-and sigma updates) on one synthetic LP that is already resident in HBM.
-  value        iterations/s over exactly K timed steps (CUDA events on the engine stream, max over ranks)
-  e2e          iterations/s through the reference-facing C ABI: solve(model, param) with HOST arrays --
-               H2D of the model, scaling, power iteration, the loop to KKT < 1e-4, D2H of x,y,z all timed
+One "step" = ITERS_PER_STEP (100) consecutive HPR iterations of the full driver (fused x/y phase kernels, the check
+iterations and residual passes the reference's schedule puts among them, restarts and sigma updates) on one synthetic
+LP that is already resident in HBM.
+  value        HPR iterations/s over exactly K timed steps (CUDA events on the engine stream, max over ranks)
+  e2e          the same metric through the reference-facing C ABI: solve(model, param) with HOST arrays -- H2D of the
+               model, device transposition, scaling, power iteration, the loop to KKT < 1e-4, D2H of x,y,z all timed
   roofline     the slower of the two fused SpMV+prox kernels, timed alone with CUDA events
-  cpu_baseline the CPU oracle (OpenMP port) on a bounded sample of the same workload
---impl reference runs the UNMODIFIED reference (its own CUDA build, oracle/_ref/libhprlp_ref.so -- the
-reference has no CPU path, BASELINE.json) through the same solve() call on the same LP.
-N > 1: the single-instance path does not shard, so every rank runs an independent replica of the same
-workload ("replicas only") and `value` is the sum; no collective on the data path.
+  cpu_baseline the CPU oracle (OpenMP port) on a bounded sample of the same workload (N = 1 only)
+  batched      configs[3] (solve_batched shared-A, B = 256), batch-sharded over the N GPUs: instance-iterations/s
+  parity       (N > 1) asserted in the run: a small LP solved row-partitioned over the N GPUs vs on one GPU, and a
+               batch solved sharded vs unsharded
+--impl reference runs the UNMODIFIED reference (its own CUDA build, oracle/_ref/libhprlp_ref.so -- the reference has
+no CPU path, BASELINE.json) through the same solve() call on the same LP; it is single-GPU, so rank 0 alone runs it.
+
+N > 1 (torchrun, one process per GPU): the SAME LP (configs[2], nnz = 1e8) is solved ROW-PARTITIONED over the N GPUs --
+GPU p owns a block of rows of A and an x-block; per iteration one reduce-scatter of the partial A^T y and one all-gather
+of the x_hat blocks (NCCL over NVLink).  `value` is the iteration rate of that one solve ("scaling": "strong": total
+work fixed), `partitioned.speedup_vs_1gpu` is measured against the 1-GPU engine in the same run, `batched` carries
+configs[3] sharded over the N GPUs, and at N = 8 `c5` carries configs[4] (nnz = 6e9, does not fit one GPU).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -38,23 +46,43 @@ ITERS_PER_STEP = 100
 PREROLL = 1000
 
 WORKLOADS = {
+    # BASELINE.json configs[0]: the bundled toy LP through the CLI with default parameters (presolve on)
+    "c1": dict(kind="mps", name="configs[0]: bundled data/model.mps (m=n=2), CLI defaults incl. presolve, tol 1e-4"),
     # BASELINE.json configs[1]: synthetic uniform-density LP m=1e5 n=1e6 nnz=1e7
     "c2": dict(kind="uniform", m=100_000, n=1_000_000, nnz=10_000_000,
                name="configs[1]: synthetic uniform LP m=1e5 n=1e6 nnz=1e7, tol 1e-4"),
     # BASELINE.json configs[2]: synthetic power-law LP m=2e6 n=5e6 nnz=1e8
     "c3": dict(kind="powerlaw", m=2_000_000, n=5_000_000, nnz=100_000_000,
                name="configs[2]: synthetic power-law LP m=2e6 n=5e6 nnz=1e8, tol 1e-4"),
+    # the same kernels on a STRUCTURED matrix of configs[2]'s size: columns of row i lie in a window around i*n/m, so
+    # gathers coalesce into few sectors (shows what the kernels reach when the input has locality)
+    "c3band": dict(kind="banded", m=2_000_000, n=5_000_000, nnz=100_000_000,
+                   name="structured twin of configs[2]: banded LP m=2e6 n=5e6 nnz=1e8 (columns within a 4096-wide window)"),
     "small": dict(kind="uniform", m=5_000, n=20_000, nnz=200_000, name="debug: uniform m=5e3 n=2e4 nnz=2e5"),
     # BASELINE.json configs[3]: solve_batched shared-A m=5e4 n=2e5 nnz=2e6, batch 256, batch-sharded over the GPUs
     "c4": dict(kind="uniform", m=50_000, n=200_000, nnz=2_000_000, batch=256, iters=300,
                name="configs[3]: solve_batched shared-A m=5e4 n=2e5 nnz=2e6, batch 256, batch-sharded"),
     "c4small": dict(kind="uniform", m=2_000, n=8_000, nnz=80_000, batch=64, iters=300, name="debug: batched m=2e3 n=8e3 B=64"),
 }
+C5 = dict(m=20_000_000, n=50_000_000, K=300, name="configs[4]: synthetic uniform LP nnz=6e9 (m=2e7 n=5e7, 300 per row), row-block partitioned")
+PARITY_LP = dict(kind="powerlaw", m=20_000, n=50_000, nnz=1_000_000)
 
 
 def algorithmic_bytes(m, n, nnz):
     """per normal iteration 24 nnz + 68 n + 52 m; x-phase 12 nnz + 60 n + 8 m; y-phase 12 nnz + 44 m + 8 n."""
     return dict(iter=24 * nnz + 68 * n + 52 * m, x=12 * nnz + 60 * n + 8 * m, y=12 * nnz + 44 * m + 8 * n)
+
+
+def measured_peak():
+    pk_file = ROOT / "MEASURED_PEAKS.json"
+    if pk_file.exists():
+        try:
+            peaks = json.loads(pk_file.read_text())
+            if "hbm_gbs" in peaks:
+                return float(peaks["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
 
 
 class ClockSampler:
@@ -108,6 +136,22 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
+class Quiet:
+    """The libraries print their logs to stdout (std::cout / printf): keep stdout clean for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.devnull = os.open(os.devnull, os.O_WRONLY)
+        self.saved = os.dup(1)
+        os.dup2(self.devnull, 1)
+        return self
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.devnull)
+        os.close(self.saved)
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -140,66 +184,75 @@ def reduce_max_sum(dist, local, ms, units):
     return float(t.item()), float(u.item())
 
 
+def fresh_uid(eng, dist, rank, local):
+    """A new NCCL unique id made by rank 0 and broadcast with torch.distributed: one per communicator of the engine."""
+    return graft.load_package().broadcast_unique_id(dist, eng.nccl_unique_id, rank)
+
+
 def cpu_baseline(pkg, lp, iters=10):
-    import ctypes as C
     O = pkg.load_oracle()
     f = O.lib.oracle_time_iterations
-    f.restype = C.c_double
-    thr = C.c_int(0)
+    f.restype = ctypes.c_double
+    thr = ctypes.c_int(0)
     ip, dp = pkg._ip, pkg._dp
     secs = f(lp["m"], lp["n"], ip(lp["rowPtr"]), ip(lp["colIndex"]), dp(lp["values"]), dp(lp["AL"]), dp(lp["AU"]), dp(lp["l"]),
-             dp(lp["u"]), dp(lp["c"]), iters, C.byref(thr))
+             dp(lp["u"]), dp(lp["c"]), iters, ctypes.byref(thr))
     return dict(value=iters / secs, unit="HPR iterations/s", cores=int(thr.value), kind="port",
                 sample=f"{iters} HPR iterations (fused x+y phase, unscaled data) of the same LP by oracle/hpr_oracle.c, OpenMP over rows")
 
 
-def run_engine_arm(args, pkg, spec, lp, rank, world, local, dist):
+def make_lp(pkg, spec):
+    return pkg.synth_lp(spec["kind"], spec["m"], spec["n"], spec["nnz"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# resident engine, CUDA-event timed: the `value` of both the 1-GPU and the row-partitioned arm
+# ----------------------------------------------------------------------------------------------------------------
+def time_resident_engine(eng, pkg, h, steps, warmup, dist, local, profile=False):
+    info = pkg.B200Info()
+    eng.lib.hprlp_b200_engine_run(h, PREROLL)
+    for _ in range(warmup):
+        eng.lib.hprlp_b200_engine_run(h, ITERS_PER_STEP)
+    eng.lib.hprlp_b200_engine_info(h, ctypes.byref(info))
+    launches0 = info.kernel_launches
+    barrier(dist, local)
+    if profile:
+        eng.lib.hprlp_b200_profiler_start()      # no-op unless run under `ncu --profile-from-start off`
+    with ClockSampler(local) as clk:
+        t_wall = time.perf_counter()
+        ms = 0.0
+        for _ in range(steps):
+            ms += eng.lib.hprlp_b200_engine_run(h, ITERS_PER_STEP)     # CUDA events on the engine stream
+        wall_ms = (time.perf_counter() - t_wall) * 1e3
+    if profile:
+        eng.lib.hprlp_b200_profiler_stop()
+    barrier(dist, local)
+    eng.lib.hprlp_b200_engine_info(h, ctypes.byref(info))
+    return dict(ms=max(ms, 0.0), wall_ms=wall_ms, launches=int(info.kernel_launches - launches0), clocks=clk.summary(), info=info)
+
+
+def run_engine_arm(args, pkg, spec, lp, local):
+    """N = 1: the whole LP on one GPU."""
     eng = pkg.load_engine()          # no fallback: raises if lib/libhprlp.so is missing
     m, n, nnz = lp["m"], lp["n"], int(lp["values"].shape[0])
     param = pkg.Parameters.default(stop_tol=0.0, use_presolve=False, device_number=local)   # tol 0: the loop never stops
     model = eng.create_model(lp)
-    h = eng.lib.hprlp_b200_engine_create(model, __import__("ctypes").byref(param))
+    h = eng.lib.hprlp_b200_engine_create(model, ctypes.byref(param))
     if not h:
         raise RuntimeError("engine_create failed")
-    info = pkg.B200Info()
+    warm = max(args.warmup, 3)
     # pre-roll (untimed): the first PREROLL iterations carry a residual check every 10 iterations, afterwards every
     # 100 (reference schedule, src/utils.cu:100-102).  The timed window starts in the steady regime, the same
     # window the reference arm's `value` is taken from (iterations 1000..3000).
-    eng.lib.hprlp_b200_engine_run(h, PREROLL)
-    for _ in range(max(args.warmup, 3)):
-        eng.lib.hprlp_b200_engine_run(h, ITERS_PER_STEP)
-    eng.lib.hprlp_b200_engine_info(h, __import__("ctypes").byref(info))
-    launches0 = info.kernel_launches
-    barrier(dist, local)
-    eng.lib.hprlp_b200_profiler_start()      # no-op unless run under `ncu --profile-from-start off`
-    with ClockSampler(local) as clk:
-        t_wall = time.perf_counter()
-        ms = 0.0
-        for _ in range(args.steps):
-            ms += eng.lib.hprlp_b200_engine_run(h, ITERS_PER_STEP)     # CUDA events on the engine stream
-        wall_ms = (time.perf_counter() - t_wall) * 1e3
-    eng.lib.hprlp_b200_profiler_stop()
-    barrier(dist, local)
-    eng.lib.hprlp_b200_engine_info(h, __import__("ctypes").byref(info))
-    launches = int(info.kernel_launches - launches0)
+    t = time_resident_engine(eng, pkg, h, args.steps, warm, None, local, profile=True)
     iters = args.steps * ITERS_PER_STEP
-    ms_max, iters_sum = reduce_max_sum(dist, local, max(ms, 0.0), iters)
     # roofline: each fused kernel alone, back to back, CUDA events (inputs > L2 for c2/c3: no flush needed)
     tx = eng.lib.hprlp_b200_engine_time_phase(h, 0, 50)
     ty = eng.lib.hprlp_b200_engine_time_phase(h, 1, 50)
     eng.lib.hprlp_b200_engine_destroy(h)
     eng.free_model(model)
-    if rank != 0:
-        return None
     ab = algorithmic_bytes(m, n, nnz)
-    peaks = {}
-    pk_file = ROOT / "MEASURED_PEAKS.json"
-    peak_src = "fallback"
-    peak = 6650.0
-    if pk_file.exists():
-        peaks = json.loads(pk_file.read_text())
-        if "hbm_gbs" in peaks:
-            peak, peak_src = float(peaks["hbm_gbs"]), "measured"
+    peak, peak_src = measured_peak()
     dom = "y" if ty >= tx else "x"
     dur_ms = ty if dom == "y" else tx
     achieved = ab[dom] / (dur_ms * 1e-3) / 1e9
@@ -215,7 +268,7 @@ def run_engine_arm(args, pkg, spec, lp, rank, world, local, dist):
     # FMA on this launch shape (tools/gather_bench.cu, SPMV_TEX) = 262e9 nnz/s with the gathered vector resident in L2.
     port = None
     gc = ROOT / "profiles" / "r1_gather_ceiling.json"
-    if gc.exists():
+    if gc.exists() and spec["kind"] != "banded":
         try:
             rows = [r for r in json.loads(gc.read_text())["results"] if r["mode"] == "SPMV_TEX"]
             vec = m if dom == "x" else n     # x-phase gathers y (m entries), y-phase gathers x_hat (n entries)
@@ -231,19 +284,121 @@ def run_engine_arm(args, pkg, spec, lp, rank, world, local, dist):
                 algorithmic_bytes_per_launch=ab[dom], launch_ms=dur_ms,
                 x_phase=dict(ms=tx, gbs=ab["x"] / (tx * 1e-3) / 1e9), y_phase=dict(ms=ty, gbs=ab["y"] / (ty * 1e-3) / 1e9),
                 iteration_gbs=ab["iter"] / ((tx + ty) * 1e-3) / 1e9)
+    info = t["info"]
+    return dict(metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
+                value=iters / (t["ms"] * 1e-3), unit="HPR iterations/s", n_gpus=1, steps=args.steps, warmup=warm,
+                ms_per_step=t["ms"] / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload=spec["name"], m=m, n=n, nnz=nnz, iters_per_step=ITERS_PER_STEP,
+                            window="timed steps start at HPR iteration %d (steady regime: residual check every 100 iterations)" % (PREROLL + ITERS_PER_STEP * warm),
+                            l2="per-iteration working set %.0f MB > 126 MB L2 (no flush)" % (ab["iter"] / 1e6),
+                            parallelism="1 GPU", lanes_A=info.lanes_A, lanes_AT=info.lanes_AT),
+                gpu_launches=t["launches"], wall_ms_per_step=t["wall_ms"] / args.steps, clocks=t["clocks"], roofline=roof)
+
+
+def run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist):
+    """N > 1: ONE LP row-partitioned over the N GPUs, one process per GPU (this process = row block `rank`)."""
+    eng = pkg.load_engine()
+    m, n, nnz = lp["m"], lp["n"], int(lp["values"].shape[0])
+    param = pkg.Parameters.default(stop_tol=0.0, use_presolve=False, device_number=local)
+    model = eng.create_model(lp)
+    uid = fresh_uid(eng, dist, rank, local)
+    h = eng.lib.hprlp_b200_engine_create_rank(model, ctypes.byref(param), uid, rank, world)
+    if not h:
+        raise RuntimeError("engine_create_rank failed")
+    warm = max(args.warmup, 3)
+    t = time_resident_engine(eng, pkg, h, args.steps, warm, dist, local)
+    iters = args.steps * ITERS_PER_STEP
+    ms_max, _ = reduce_max_sum(dist, local, t["ms"], 0)
+    # per-GPU pieces of one iteration, each timed alone (CUDA events, max over ranks)
+    parts = {}
+    for name, which in (("partial_ATy_pass", 2), ("exchange_reduce_scatter_all_gather", 4), ("x_update_block", 3), ("y_phase", 1)):
+        barrier(dist, local)
+        v = eng.lib.hprlp_b200_engine_time_phase(h, which, 30)
+        parts[name + "_ms"], _ = reduce_max_sum(dist, local, v, 0)
+    eng.lib.hprlp_b200_engine_destroy(h)
+    eng.free_model(model)
+    # the 1-GPU engine on the same LP in the same run (rank 0; the others wait): the denominator of speedup_vs_1gpu
+    one_gpu = None
+    if rank == 0 and not args.no_single_ref:
+        h1 = eng.lib.hprlp_b200_engine_create(model_or_new(eng, lp), ctypes.byref(param))
+        t1 = time_resident_engine(eng, pkg, h1, max(3, args.steps // 2), 3, None, local)
+        one_gpu = (max(3, args.steps // 2) * ITERS_PER_STEP) / (t1["ms"] * 1e-3)
+        eng.lib.hprlp_b200_engine_destroy(h1)
+        eng.release_cached_memory()
+    barrier(dist, local)
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    ms_iter = ms_max / iters
+    # algorithmic bytes per GPU per iteration: its share of both matrix passes and of the y-side vectors, the x-side
+    # vectors of ITS x-block (68 n / P: counted once over the node), plus what the row partition itself requires on
+    # every GPU: the full x_hat gathered by the y-phase (8 n) and the partial w = A_p^T y_p (row pointers of the n-row
+    # transpose 4 n, write 8 n).
+    per_gpu = (24 * nnz + 52 * m + 68 * n) / world + 20 * n
+    roof = dict(bound="hbm", achieved=per_gpu / (ms_iter * 1e-3) / 1e9, peak=peak, unit="GB/s", frac=per_gpu / (ms_iter * 1e-3) / 1e9 / peak,
+                traffic=None, peak_source=peak_src, kernel="whole partitioned iteration per GPU (A_p^T pass + exchange + x-update + fused y-phase)",
+                algorithmic_bytes_per_gpu_per_iteration=per_gpu, nvlink_bytes_per_gpu_per_iteration=2 * 8 * n * (world - 1) / world,
+                **parts)
+    info = t["info"]
     out = dict(metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
-               value=iters_sum / (ms_max * 1e-3), unit="HPR iterations/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-               ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-               data="synthetic",
+               value=iters / (ms_max * 1e-3), unit="HPR iterations/s", n_gpus=world, steps=args.steps, warmup=warm,
+               ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=spec["name"], m=m, n=n, nnz=nnz, iters_per_step=ITERS_PER_STEP,
-                           window="timed steps start at HPR iteration %d (steady regime: residual check every 100 iterations)" % (PREROLL + ITERS_PER_STEP * max(args.warmup, 3)),
-                           l2="per-iteration working set %.0f MB > 126 MB L2 (no flush)" % (ab["iter"] / 1e6),
-                           parallelism="replicas only" if world > 1 else "1 GPU",
+                           window="timed steps start at HPR iteration %d (steady regime)" % (PREROLL + ITERS_PER_STEP * warm),
+                           l2="per-GPU per-iteration working set %.0f MB > 126 MB L2 (no flush)" % (per_gpu / 1e6),
+                           parallelism="row-block partitioned over %d GPUs (one process per GPU): reduce-scatter of partial A^T y + all-gather of x_hat "
+                                       "blocks per iteration, NCCL over NVLink; x-block ownership" % world,
                            lanes_A=info.lanes_A, lanes_AT=info.lanes_AT),
-               gpu_launches=launches, wall_ms_per_step=wall_ms / args.steps, clocks=clk.summary(), roofline=roof)
+               gpu_launches=t["launches"], wall_ms_per_step=t["wall_ms"] / args.steps, clocks=t["clocks"], roofline=roof,
+               partitioned=dict(ms_per_iteration=ms_iter, iters_per_s=1e3 / ms_iter, one_gpu_iters_per_s=one_gpu,
+                                speedup_vs_1gpu=(1e3 / ms_iter) / one_gpu if one_gpu else None, **parts))
     return out
 
 
+def model_or_new(eng, lp):
+    model_or_new.keep = eng.create_model(lp)     # kept alive until the process ends (bench only)
+    return model_or_new.keep
+
+
+def run_e2e(pkg, lib, lp, local, tol=1e-4):
+    """solve() through the C ABI with host arrays: H2D + setup + scaling + power iteration + loop + D2H timed."""
+    param = pkg.Parameters.default(stop_tol=tol, use_presolve=False, device_number=local)
+    model = lib.create_model(lp)
+    t0 = time.perf_counter()
+    r = lib.solve(model, param)
+    wall = time.perf_counter() - t0
+    lib.free_model(model)
+    nnz = int(lp["values"].shape[0])
+    h2d = 12 * nnz + 4 * (lp["m"] + 1) + 8 * (2 * lp["m"] + 3 * lp["n"])   # A only: A^T is built on the device
+    d2h = 8 * (2 * lp["n"] + lp["m"])
+    return dict(value=r["iter"] / wall, unit="HPR iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                time_to_tol_s=wall, solver_time_s=r["time"], iters=r["iter"], status=r["status"], primal_obj=r["primal_obj"],
+                residuals=r["residuals"], tol=tol)
+
+
+def run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist, tol=1e-4):
+    """The partitioned solve through the C ABI with HOST arrays on every rank (each uploads its row block)."""
+    param = pkg.Parameters.default(stop_tol=tol, use_presolve=False, device_number=local)
+    model = eng.create_model(lp)
+    uid = fresh_uid(eng, dist, rank, local)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    r = eng.solve_partitioned_rank(model, param, uid, rank, world)
+    wall = time.perf_counter() - t0
+    eng.free_model(model)
+    wall_max, _ = reduce_max_sum(dist, local, wall, 0)
+    nnz = int(lp["values"].shape[0])
+    return dict(value=r["iter"] / wall_max, unit="HPR iterations/s",
+                h2d_bytes_per_step=(12 * nnz + 16 * lp["m"]) // world + 24 * lp["n"] + 4 * (lp["m"] // world + 1),
+                d2h_bytes_per_step=8 * (2 * lp["n"] + lp["m"]),
+                time_to_tol_s=wall_max, solver_time_s=r["time"], iters=r["iter"], status=r["status"], primal_obj=r["primal_obj"],
+                residuals=r["residuals"], tol=tol, power_iters=r["info"]["power_iters"], power_seconds=r["info"]["power_seconds"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# solve_batched (configs[3])
+# ----------------------------------------------------------------------------------------------------------------
 def make_batch(pkg, spec, lo, hi):
     """Shared matrix + instances lo..hi-1 (instance k draws its primal-dual pair with seed+k)."""
     base = pkg.synth_lp(spec["kind"], spec["m"], spec["n"], spec["nnz"])
@@ -279,7 +434,16 @@ def run_batched(args, pkg, spec, lib, rank, world, local, dist, impl):
     if rank != 0:
         return None
     m, n, nnz = base["m"], base["n"], int(base["values"].shape[0])
+    peak, peak_src = measured_peak()
     bytes_iter = 24 * nnz + 4 * (n + m) + B * (64 * n + 48 * m)    # SURVEY.md 8(d), whole batch, A streamed once
+    per_gpu_gbs = bytes_iter * spec["iters"] / (t_solve * 1e-3) / 1e9 / world
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("c4", {}).get("iteration")
+        except Exception:
+            traffic = None
     out = dict(metric="HPR instance-iterations/s, solve_batched shared-A", value=units / (t_solve * 1e-3), unit="instance-iterations/s",
                n_gpus=world, steps=steps, warmup=warm, ms_per_step=t_solve, higher_is_better=True, scaling="strong", vs_baseline=None,
                dtype="f64", data="synthetic", impl=impl,
@@ -288,10 +452,129 @@ def run_batched(args, pkg, spec, lib, rank, world, local, dist, impl):
                            l2="batched vectors %.0f MB >> 126 MB L2" % (B * (64 * n + 48 * m) / 1e6)),
                e2e=dict(value=units / (t_wall * 1e-3), unit="instance-iterations/s",
                         h2d_bytes_per_step=8 * (hi - lo) * (3 * n + 2 * m) + 24 * nnz, d2h_bytes_per_step=8 * (hi - lo) * (2 * n + m)),
-               roofline=dict(bound="hbm", achieved=bytes_iter * spec["iters"] / (t_solve * 1e-3) / 1e9 / world, peak=6549.1, unit="GB/s",
-                             frac=bytes_iter * spec["iters"] / (t_solve * 1e-3) / 1e9 / world / 6549.1, traffic=None,
+               roofline=dict(bound="hbm", achieved=per_gpu_gbs, peak=peak, unit="GB/s", frac=per_gpu_gbs / peak, traffic=traffic,
+                             peak_source=peak_src,
                              note="whole loop (fused SpMM+prox x/y kernels + checks); per GPU; algorithmic bytes 24nnz+4(n+m)+B(64n+48m)"),
                clocks=clk.summary(), gpu_launches=None)
+    return out
+
+
+def batched_summary(b):
+    if b is None:
+        return None
+    return dict(workload=b["config"]["workload"], instance_iterations_per_s=b["value"], e2e_instance_iterations_per_s=b["e2e"]["value"],
+                solve_ms=b["ms_per_step"], n_gpus=b["n_gpus"], roofline_frac_per_gpu=b["roofline"]["frac"], batch=b["config"]["batch"],
+                iters=b["config"]["iters_per_step"], parallelism=b["config"]["parallelism"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# in-run parity of the multi-GPU paths (N > 1)
+# ----------------------------------------------------------------------------------------------------------------
+def run_parity(pkg, eng, rank, world, local, dist):
+    out = {}
+    lp = pkg.synth_lp(PARITY_LP["kind"], PARITY_LP["m"], PARITY_LP["n"], PARITY_LP["nnz"])
+    ok_all = True
+    cases = []
+    for prm in (dict(stop_tol=1e-6), dict(max_iter=300, stop_tol=1e-30)):
+        p = pkg.Parameters.default(use_presolve=False, device_number=local, **prm)
+        model = eng.create_model(lp)
+        one = eng.solve(model, p, main=True)
+        uid = fresh_uid(eng, dist, rank, local)
+        par = eng.solve_partitioned_rank(model, p, uid, rank, world)
+        eng.free_model(model)
+        err = max(float(np.max(np.abs(one[k] - par[k])) / max(1.0, float(np.max(np.abs(one[k]))))) for k in "xyz")
+        ok = one["status"] == par["status"] and one["iter"] == par["iter"] and err <= 1e-8
+        cases.append(dict(params=prm, status=[one["status"], par["status"]], iters=[one["iter"], par["iter"]], max_rel_err_xyz=err, ok=bool(ok)))
+        ok_all = ok_all and ok
+    out["partitioned_vs_single_gpu"] = dict(lp=PARITY_LP, tolerance=1e-8, cases=cases, ok=bool(ok_all))
+    # sharded vs unsharded batch
+    spec = WORKLOADS["c4small"]
+    B = spec["batch"]
+    lo, hi = pkg.shard_range(B, world, rank)
+    base, d = make_batch(pkg, spec, 0, B)
+    p = pkg.Parameters.default(stop_tol=1e-6, max_iter=2000, use_presolve=False, device_number=local)
+    model = eng.create_model(base)
+    mine = eng.solve_batched(model, d["C"][lo:hi], d["AL"][lo:hi], d["AU"][lo:hi], d["l"][lo:hi], d["u"][lo:hi], None, p)
+    xs = pkg.gather_shards(dist, mine["x"], B, world, rank)
+    its = pkg.gather_shards(dist, mine["iter"].astype(np.float64).reshape(-1, 1), B, world, rank)
+    bok, berr = True, 0.0
+    if rank == 0:
+        full = eng.solve_batched(model, d["C"], d["AL"], d["AU"], d["l"], d["u"], None, p)
+        berr = float(np.max(np.abs(full["x"] - xs)) / max(1.0, float(np.max(np.abs(full["x"])))))
+        bok = bool(np.array_equal(full["iter"], its.reshape(-1).astype(full["iter"].dtype)) and berr <= 1e-9)
+    eng.free_model(model)
+    out["batch_sharded_vs_unsharded"] = dict(workload=spec["name"], tolerance=1e-9, max_rel_err_x=berr, iteration_arrays_equal=bok, ok=bool(bok))
+    out["ok"] = bool(ok_all and bok)
+    flag, _ = reduce_max_sum(dist, local, 0.0 if out["ok"] else 1.0, 0)
+    out["ok_all_ranks"] = flag == 0.0
+    return out
+
+
+def run_c5(pkg, eng, rank, world, local, dist):
+    """configs[4]: nnz = 6e9, generated shard by shard on the GPUs, row-partitioned, solved to KKT < 1e-4."""
+    p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-4, time_limit=300.0, device_number=local)
+    uid = fresh_uid(eng, dist, rank, local)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    r = eng.solve_partitioned_synth_rank(C5["m"], C5["n"], C5["K"], p, uid, rank, world, want_solution=False)
+    wall = time.perf_counter() - t0
+    wall, _ = reduce_max_sum(dist, local, wall, 0)
+    if rank != 0:
+        return None
+    i = r["info"]
+    nnz = C5["m"] * C5["K"]
+    ms_it = i["loop_device_ms"] / max(r["iter"], 1)
+    per_gpu = (24 * nnz + 52 * C5["m"] + 68 * C5["n"]) / world + 20 * C5["n"]
+    peak, _ = measured_peak()
+    return dict(workload=C5["name"], m=C5["m"], n=C5["n"], nnz=nnz, n_gpus=world, status=r["status"], iters=r["iter"],
+                primal_obj=r["primal_obj"], constructed_optimum=r["obj_star"],
+                rel_obj_error=abs(r["primal_obj"] - r["obj_star"]) / (1 + abs(r["obj_star"])), residuals=r["residuals"],
+                wall_s=wall, generate_and_transpose_s=i["setup_seconds"], scaling_s=i["scaling_seconds"], power_s=i["power_seconds"],
+                power_iters=i["power_iters"], time_to_1e4_s=r["time"], ms_per_iteration=ms_it, iters_per_s=1e3 / ms_it,
+                roofline_frac_per_gpu=per_gpu / (ms_it * 1e-3) / 1e9 / peak, bands_A=i["bands_A"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# configs[0]: the CLI on the bundled toy LP, cold process, default parameters
+# ----------------------------------------------------------------------------------------------------------------
+def run_cli(binary, mps, extra=()):
+    t0 = time.perf_counter()
+    pr = subprocess.run([str(binary), "-i", str(mps), *extra], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    wall = time.perf_counter() - t0
+    it, tm, status, obj = None, None, None, None
+    for ln in pr.stdout.splitlines():
+        s = ln.strip()
+        if s.startswith("Iterations:"):
+            it = int(s.split(":")[1])
+        elif s.startswith("Time:"):
+            tm = float(s.split(":")[1].split()[0])
+        elif s.startswith("Status:"):
+            status = s.split(":")[1].strip()
+        elif s.startswith("Primal Objective:"):
+            obj = float(s.split(":")[1])
+    return dict(wall_s=wall, iters=it, solver_time_s=tm, status=status, primal_obj=obj, returncode=pr.returncode)
+
+
+def run_c1(args, impl):
+    spec = WORKLOADS["c1"]
+    mps = ROOT / "tests" / "golden" / "model.mps"
+    binary = ROOT / "build" / "solve_mps_file" if impl == "ours" else ROOT / "oracle" / "_ref" / "solve_mps_file"
+    if not binary.exists():
+        return dict(impl=impl, unavailable=f"{binary.relative_to(ROOT)} was not built")
+    runs = [run_cli(binary, mps) for _ in range(max(2, min(args.steps, 5)))]
+    best = min(runs, key=lambda r: r["wall_s"])
+    out = dict(metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
+               value=(best["iters"] or 0) / max(best["solver_time_s"] or 1e-2, 1e-2), unit="HPR iterations/s", n_gpus=1, steps=len(runs), warmup=0,
+               ms_per_step=1e3 * best["wall_s"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="bundled",
+               config=dict(workload=spec["name"], note="each step = one cold CLI process (CUDA context, MPS parse, PSLP presolve, solve); "
+                           "value = iterations / the CLI's printed solver time (2 decimals, floored at 0.01 s); e2e = iterations / process wall"),
+               e2e=dict(value=(best["iters"] or 0) / best["wall_s"], unit="HPR iterations/s", h2d_bytes_per_step=0 if impl == "reference" else 4 * 12 + 6 * 16,
+                        d2h_bytes_per_step=0 if impl == "reference" else 48, time_to_tol_s=best["wall_s"], iters=best["iters"], status=best["status"],
+                        primal_obj=best["primal_obj"]),
+               all_runs=runs, gpu_launches=None, roofline=None)
+    if impl == "reference":
+        out["impl"] = "reference"
+        out["cpu_baseline"] = dict(value=out["value"], unit="HPR iterations/s", cores=1, kind="reference", sample="the reference CLI (its own CUDA build) on data/model.mps")
     return out
 
 
@@ -312,21 +595,33 @@ def steady_state_rate(pkg, lib, lp, local, k1=1000, k2=None):
     return (k2 - k1) / max(ts[1] - ts[0], 1e-9), ts
 
 
-def run_e2e(pkg, lib, lp, local, tol=1e-4):
-    """solve() through the C ABI with host arrays: H2D + setup + scaling + power iteration + loop + D2H timed."""
-    import contextlib, io
-    param = pkg.Parameters.default(stop_tol=tol, use_presolve=False, device_number=local)
-    model = lib.create_model(lp)
-    t0 = time.perf_counter()
-    r = lib.solve(model, param)
-    wall = time.perf_counter() - t0
-    lib.free_model(model)
-    nnz = int(lp["values"].shape[0])
-    h2d = 12 * nnz + 4 * (lp["m"] + 1) + 8 * (2 * lp["m"] + 3 * lp["n"])   # A only: A^T is built on the device
-    d2h = 8 * (2 * lp["n"] + lp["m"])
-    return dict(value=r["iter"] / wall, unit="HPR iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                time_to_tol_s=wall, solver_time_s=r["time"], iters=r["iter"], status=r["status"], primal_obj=r["primal_obj"],
-                residuals=r["residuals"], tol=tol)
+def run_reference_arm(args, pkg, spec, local):
+    lp = make_lp(pkg, spec)
+    if not pkg.REF_LIB_PATH.exists():
+        return dict(impl="reference", unavailable="oracle/_ref/libhprlp_ref.so was not built (needs /root/reference at build time)")
+    ref = pkg.load_reference()
+    with Quiet():
+        with ClockSampler(local) as clk:
+            runs = [run_e2e(pkg, ref, lp, local) for _ in range(max(1, min(args.steps, 3)))]
+            rate, rate_ts = steady_state_rate(pkg, ref, lp, local)
+    best = max(runs, key=lambda r: r["value"])
+    return dict(impl="reference", metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
+                value=rate, unit="HPR iterations/s", n_gpus=1, steps=len(runs), warmup=0,
+                ms_per_step=1e3 * ITERS_PER_STEP / rate, steady_state=dict(
+                    how="(k2-k1) iterations / (results.time[max_iter=k2] - results.time[max_iter=k1]), k1=1000, k2-k1=2000 (nnz>=5e7) or 20000",
+                    times=rate_ts,
+                    window_note="the reference can only be driven through solve(): its value is a difference of two host-clock results.time "
+                                "(iterations 1000..3000); our arm's value is CUDA events over iterations 1300..2300 of a resident engine -- same "
+                                "steady regime (one residual check per 100 iterations), different clocks"),
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=spec["name"], m=lp["m"], n=lp["n"], nnz=int(lp["values"].shape[0]),
+                                              note="value = steady-state loop rate from two max_iter runs; e2e = one solve() call to KKT<1e-4 through the reference's own C API; "
+                                                   "the reference is single-GPU: at --gpus N > 1 this line is still its 1-GPU run"),
+                cpu_baseline=dict(value=rate, unit="HPR iterations/s", cores=1, kind="reference",
+                                  sample="the reference has no CPU path (BASELINE.json): this arm is its own CUDA build "
+                                         "(oracle/_ref/libhprlp_ref.so, autotuned fused/cuSPARSE backend) on the same B200, driven by one "
+                                         "host thread; value = the line's steady-state loop rate, e2e = whole solve() calls to KKT<1e-4"),
+                e2e=dict(best, h2d_bytes_per_step=0, d2h_bytes_per_step=0), clocks=clk.summary(), all_runs=runs)
 
 
 def main():
@@ -338,11 +633,19 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))   # configs[2]: the LP BASELINE.json's target is quoted on
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the configs[3] solve_batched leg of the default line")
+    ap.add_argument("--no-c5", action="store_true", help="skip configs[4] (nnz = 6e9) at --gpus 8")
+    ap.add_argument("--no-single-ref", action="store_true", help="N > 1: skip the 1-GPU run that speedup_vs_1gpu is measured against")
     args = ap.parse_args()
 
     pkg = graft.load_package()
     rank, world, local, dist = dist_setup(args.gpus)
     spec = WORKLOADS[args.workload]
+
+    if spec["kind"] == "mps":
+        if rank == 0:
+            print(json.dumps(run_c1(args, args.impl)))
+        return 0
 
     if "batch" in spec:
         lib = pkg.load_engine() if args.impl == "ours" else (pkg.load_reference() if pkg.REF_LIB_PATH.exists() else None)
@@ -352,12 +655,8 @@ def main():
             return 0
         if args.impl == "reference":
             world, dist = 1, None          # the reference is single-GPU: rank 0 runs the whole batch
-        sys.stdout.flush()
-        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
-        try:
+        with Quiet():
             out = run_batched(args, pkg, spec, lib, rank, world, local, dist, args.impl)
-        finally:
-            os.dup2(saved, 1); os.close(devnull); os.close(saved)
         if rank == 0:
             print(json.dumps(out))
         if dist is not None:
@@ -365,64 +664,57 @@ def main():
         return 0
 
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        lp = pkg.synth_lp(spec["kind"], spec["m"], spec["n"], spec["nnz"])
-        if not pkg.REF_LIB_PATH.exists():
-            print(json.dumps(dict(impl="reference", unavailable="oracle/_ref/libhprlp_ref.so was not built (needs /root/reference at build time)")))
-            return 0
-        ref = pkg.load_reference()
-        sys.stdout.flush()
-        # the reference prints its log with std::cout: keep stdout clean for the JSON line
-        devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
-        try:
-            with ClockSampler(local) as clk:
-                runs = [run_e2e(pkg, ref, lp, local) for _ in range(max(1, min(args.steps, 3)))]
-                rate, rate_ts = steady_state_rate(pkg, ref, lp, local)
-        finally:
-            os.dup2(saved, 1); os.close(devnull); os.close(saved)
-        best = max(runs, key=lambda r: r["value"])
-        out = dict(impl="reference", metric="HPR iterations/s (time-to-1e-4 KKT in e2e); fused SpMV+prox HBM GB/s in roofline",
-                   value=rate, unit="HPR iterations/s", n_gpus=1, steps=len(runs), warmup=0,
-                   ms_per_step=1e3 * ITERS_PER_STEP / rate, steady_state=dict(
-                       how="(k2-k1) iterations / (results.time[max_iter=k2] - results.time[max_iter=k1]), k1=1000, k2-k1=2000 (nnz>=5e7) or 20000", times=rate_ts), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                   data="synthetic", config=dict(workload=spec["name"], m=lp["m"], n=lp["n"], nnz=int(lp["values"].shape[0]),
-                                                 note="value = steady-state loop rate from two max_iter runs; e2e = one solve() call to KKT<1e-4 through the reference's own C API"),
-                   cpu_baseline=dict(value=rate, unit="HPR iterations/s", cores=1, kind="reference",
-                                     sample="the reference has no CPU path (BASELINE.json): this arm is its own CUDA build "
-                                            "(oracle/_ref/libhprlp_ref.so, autotuned fused/cuSPARSE backend) on the same B200, driven by one "
-                                            "host thread; value = the line's steady-state loop rate, e2e = whole solve() calls to KKT<1e-4"),
-                   e2e=dict(best, h2d_bytes_per_step=0, d2h_bytes_per_step=0), clocks=clk.summary(), all_runs=runs)
-        print(json.dumps(out))
+        if rank == 0:
+            print(json.dumps(run_reference_arm(args, pkg, spec, local)))
         return 0
 
-    lp = pkg.synth_lp(spec["kind"], spec["m"], spec["n"], spec["nnz"])
-    # keep the engine's own log off stdout (single JSON line contract)
-    sys.stdout.flush()
-    devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(1); os.dup2(devnull, 1)
-    try:
-        out = run_engine_arm(args, pkg, spec, lp, rank, world, local, dist)
-        e2e = None
-        if not args.no_e2e:
-            # same protocol as the reference arm: up to 3 whole solve() calls, the best one is reported (the first call of
-            # a process also loads cuRAND's kernels for the power-iteration start vector, ~0.6 s), all are listed
-            runs = [run_e2e(pkg, pkg.load_engine(), lp, local) for _ in range(max(1, min(args.steps, 3)))]
-            e = max(runs, key=lambda r: r["value"])
-            v, _ = reduce_max_sum(dist, local, 0.0, e["value"])
-            e2e = dict(e, value=_ if world > 1 else e["value"], all_runs_time_to_tol_s=[r["time_to_tol_s"] for r in runs])
-        cpu = None
-        if rank == 0 and world == 1 and not args.no_cpu:
-            cpu = cpu_baseline(pkg, lp, iters=10 if spec["nnz"] >= 5_000_000 else 200)
-    finally:
-        os.dup2(saved, 1); os.close(devnull); os.close(saved)
+    lp = make_lp(pkg, spec)
+    eng = pkg.load_engine()
+    with Quiet():
+        if world == 1:
+            out = run_engine_arm(args, pkg, spec, lp, local)
+            if not args.no_e2e:
+                # same protocol as the reference arm: up to 3 whole solve() calls, the best one is reported (the first call of
+                # a process also loads cuRAND's kernels for the power-iteration start vector, ~0.6 s), all are listed
+                runs = [run_e2e(pkg, eng, lp, local) for _ in range(max(1, min(args.steps, 3)))]
+                e = max(runs, key=lambda r: r["value"])
+                out["e2e"] = dict(e, all_runs_time_to_tol_s=[r["time_to_tol_s"] for r in runs])
+            eng.release_cached_memory()
+            if not args.no_batched and args.workload == "c3":
+                out["batched"] = batched_summary(run_batched(args, pkg, WORKLOADS["c4"], eng, 0, 1, local, None, "ours"))
+            if not args.no_cpu:
+                out["cpu_baseline"] = cpu_baseline(pkg, lp, iters=10 if spec["nnz"] >= 5_000_000 else 200)
+        else:
+            parity = run_parity(pkg, eng, rank, world, local, dist)
+            out = run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist)
+            e2e = None
+            if not args.no_e2e:
+                runs = [run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist) for _ in range(2)]
+                e2e = dict(max(runs, key=lambda r: r["value"]), all_runs_time_to_tol_s=[r["time_to_tol_s"] for r in runs])
+            eng.release_cached_memory()
+            batched = None
+            if not args.no_batched and args.workload == "c3":
+                batched = batched_summary(run_batched(args, pkg, WORKLOADS["c4"], eng, rank, world, local, dist, "ours"))
+            c5 = None
+            if world == 8 and not args.no_c5 and args.workload == "c3":
+                eng.release_cached_memory()
+                c5 = run_c5(pkg, eng, rank, world, local, dist)
+            if rank == 0:
+                out["parity"] = parity
+                if e2e is not None:
+                    out["e2e"] = e2e
+                if batched is not None:
+                    out["batched"] = batched
+                if c5 is not None:
+                    out["c5"] = c5
     if rank == 0:
-        if e2e is not None:
-            out["e2e"] = e2e
-        if cpu is not None:
-            out["cpu_baseline"] = cpu
         print(json.dumps(out))
     if dist is not None:
+        barrier(dist, local)
         dist.destroy_process_group()
+    if world > 1 and rank == 0 and not out.get("parity", {}).get("ok_all_ranks", True):
+        print("[bench] in-run parity FAILED: " + json.dumps(out["parity"]), file=sys.stderr)
+        return 1
     return 0
 
 

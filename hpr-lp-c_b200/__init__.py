@@ -92,7 +92,10 @@ REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve
 EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200_engine_create",
                     "hprlp_b200_engine_run", "hprlp_b200_engine_time_phase", "hprlp_b200_engine_residuals",
                     "hprlp_b200_engine_info", "hprlp_b200_engine_destroy", "hprlp_b200_scale_only",
-                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_solve_partitioned_synth", "hprlp_b200_synth_rows", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version"]
+                    "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_solve_partitioned_synth", "hprlp_b200_synth_rows", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version",
+                    "hprlp_b200_solve_partitioned_local", "hprlp_b200_nccl_unique_id", "hprlp_b200_solve_partitioned_rank",
+                    "hprlp_b200_engine_create_rank", "hprlp_b200_nccl_exchange_ms", "hprlp_b200_solve_partitioned_synth_rank",
+                    "hprlp_b200_release_cached_memory"]
 
 
 def _dp(a):
@@ -169,6 +172,23 @@ class HprLib:
             L.hprlp_b200_solve_partitioned.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_int, C.c_int, C.POINTER(B200Info)]
             L.hprlp_b200_solve_batched_multi.restype = BatchedResults
             L.hprlp_b200_solve_batched_multi.argtypes = L.solve_batched.argtypes + [C.c_int]
+            L.hprlp_b200_solve_partitioned_local.restype = Results
+            L.hprlp_b200_solve_partitioned_local.argtypes = L.hprlp_b200_solve_partitioned.argtypes
+            L.hprlp_b200_nccl_unique_id.restype = C.c_int
+            L.hprlp_b200_nccl_unique_id.argtypes = [C.c_char_p]
+            L.hprlp_b200_solve_partitioned_rank.restype = Results
+            L.hprlp_b200_solve_partitioned_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_char_p, C.c_int, C.c_int,
+                                                            C.c_int, C.POINTER(B200Info)]
+            L.hprlp_b200_engine_create_rank.restype = C.c_void_p
+            L.hprlp_b200_engine_create_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_char_p, C.c_int, C.c_int]
+            L.hprlp_b200_nccl_exchange_ms.restype = C.c_int
+            L.hprlp_b200_nccl_exchange_ms.argtypes = [C.c_int, C.c_longlong, C.c_int, c_double_p]
+            L.hprlp_b200_solve_partitioned_synth_rank.restype = Results
+            L.hprlp_b200_solve_partitioned_synth_rank.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(Parameters),
+                                                                  C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p,
+                                                                  C.POINTER(B200Info)]
+            L.hprlp_b200_release_cached_memory.restype = None
+            L.hprlp_b200_release_cached_memory.argtypes = []
 
     # -- model layer -----------------------------------------------------------------------------
     def create_model(self, lp, is_csc=False):
@@ -236,13 +256,52 @@ class HprLib:
         out["trace"] = {int(k): (tx[i].copy(), ty[i].copy(), tz[i].copy()) for i, k in enumerate(ti)}
         return out
 
-    def solve_partitioned(self, model, param, n_gpus, quiet=True):
+    def solve_partitioned(self, model, param, n_gpus, quiet=True, local=False):
+        """Row-partitioned solve driven from this process: n_gpus GPUs over NCCL, or (local=True) n_gpus logical ranks
+        on ONE GPU with host-synchronised exchanges (the parity-test path of 1-GPU boxes)."""
         mm = model.contents
         info = B200Info()
-        res = self.lib.hprlp_b200_solve_partitioned(model, C.byref(param), int(n_gpus), 1 if quiet else 0, C.byref(info))
+        fn = self.lib.hprlp_b200_solve_partitioned_local if local else self.lib.hprlp_b200_solve_partitioned
+        res = fn(model, C.byref(param), int(n_gpus), 1 if quiet else 0, C.byref(info))
         out = self._take(res, mm.m, mm.n)
         out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         return out
+
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        if self.lib.hprlp_b200_nccl_unique_id(buf) != 0:
+            raise RuntimeError("hprlp_b200_nccl_unique_id failed")
+        return buf.raw
+
+    def solve_partitioned_rank(self, model, param, uid, rank, nranks, quiet=True):
+        """One process per GPU: this process owns row block `rank`; every rank gets the full solution."""
+        mm = model.contents
+        info = B200Info()
+        res = self.lib.hprlp_b200_solve_partitioned_rank(model, C.byref(param), uid, int(rank), int(nranks), 1 if quiet else 0,
+                                                         C.byref(info))
+        out = self._take(res, mm.m, mm.n)
+        out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
+        return out
+
+    def solve_partitioned_synth_rank(self, m, n, K, param, uid, rank, nranks, seed=None, want_solution=False, quiet=True):
+        info = B200Info()
+        obj = C.c_double(0.0)
+        res = self.lib.hprlp_b200_solve_partitioned_synth_rank(int(m), int(n), int(K), SEED if seed is None else seed, C.byref(param),
+                                                               uid, int(rank), int(nranks), 1 if quiet else 0,
+                                                               1 if want_solution else 0, C.byref(obj), C.byref(info))
+        out = self._take(res, int(m), int(n))
+        out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
+        out["obj_star"] = obj.value
+        return out
+
+    def nccl_exchange_ms(self, n_gpus, count, reps=20):
+        out = np.zeros(2)
+        if self.lib.hprlp_b200_nccl_exchange_ms(int(n_gpus), int(count), int(reps), _dp(out)) != 0:
+            raise RuntimeError("hprlp_b200_nccl_exchange_ms failed")
+        return dict(reduce_scatter_all_gather_ms=float(out[0]), all_reduce_ms=float(out[1]))
+
+    def release_cached_memory(self):
+        self.lib.hprlp_b200_release_cached_memory()
 
     def solve_partitioned_synth(self, m, n, K, param, n_gpus, seed=None, want_solution=True, quiet=True):
         info = B200Info()
@@ -409,7 +468,9 @@ SEED = 20251018
 
 
 def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
-    """kind: 'uniform' | 'powerlaw'. Returns the dict create_model() takes (+ x*,y*,z*,obj*)."""
+    """kind: 'uniform' | 'powerlaw' | 'banded' (uniform row lengths, columns of row i within a 4096-wide window around
+    i*n/m: the structured twin used to show the kernels on coalescing gathers). Returns the dict create_model() takes
+    (+ x*,y*,z*,obj*)."""
     if not SYNTH_LIB_PATH.exists():
         raise FileNotFoundError(f"{SYNTH_LIB_PATH} not built")
     L = C.CDLL(str(SYNTH_LIB_PATH))
@@ -419,11 +480,16 @@ def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
     L.synth_lp_matrix_rows.argtypes = [C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
     L.synth_lp_vectors.restype = C.c_double
     L.synth_lp_vectors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, C.c_uint64, C.c_uint64] + [c_double_p] * 8
-    k = {"uniform": 0, "powerlaw": 1}[kind]
+    k = {"uniform": 0, "powerlaw": 1, "banded": 0}[kind]
     rp = np.zeros(m + 1, np.int32)
     tot = L.synth_lp_rowptr(k, m, n, int(nnz), seed, _ip(rp))
     col = np.zeros(tot, np.int32); val = np.zeros(tot)
-    L.synth_lp_matrix_rows(n, seed, _ip(rp), 0, m, _ip(col), _dp(val))
+    if kind == "banded":
+        L.synth_lp_matrix_rows_banded.restype = None
+        L.synth_lp_matrix_rows_banded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
+        L.synth_lp_matrix_rows_banded(m, n, 4096, seed, _ip(rp), 0, m, _ip(col), _dp(val))
+    else:
+        L.synth_lp_matrix_rows(n, seed, _ip(rp), 0, m, _ip(col), _dp(val))
     lp = dict(m=m, n=n, rowPtr=rp, colIndex=col, values=val)
     lp.update(synth_vectors(lp, seed, seed if vec_seed is None else vec_seed, _lib=L))
     if not with_solution:
@@ -473,6 +539,33 @@ def gather_shards(dist, local, B, world, rank):
     outs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf)
     return np.concatenate([outs[r][: hi - lo].cpu().numpy() for r, (lo, hi) in enumerate(sizes)], axis=0)
+
+
+def broadcast_unique_id(dist, make_id, rank):
+    """The 128-byte NCCL unique id of a new engine communicator: made by rank 0 (make_id() -> bytes), broadcast with
+    torch.distributed (one process per GPU; bench.py under torchrun).  Works on the nccl and gloo backends."""
+    import torch
+    dev = f"cuda:{torch.cuda.current_device()}" if dist.get_backend() == "nccl" else "cpu"
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        raw = make_id()
+        assert len(raw) == 128
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def row_blocks_by_nnz(rowPtr, P):
+    """Row blocks of the partitioned solve, balanced by nonzeros -- the split csrc/partitioned.cu uses
+    (block p = rows [b[p], b[p+1]))."""
+    rp = np.asarray(rowPtr, dtype=np.int64)
+    m, nnz = rp.shape[0] - 1, int(rp[-1])
+    b = [0] * (P + 1)
+    b[P] = m
+    for p in range(1, P):
+        t = nnz * p // P
+        b[p] = min(max(int(np.searchsorted(rp, t, side="left")), b[p - 1]), m)
+    return b
 
 
 def reduce_time_units(dist, ms, units):

@@ -13,6 +13,7 @@
 #include "../../include/HPRLP.h"
 #include "../../include/hprlp_b200.h"
 #include "../../include/version.h"
+#include "abi_guard.h"
 #include "engine.h"
 #include <cuda_profiler_api.h>
 
@@ -25,14 +26,7 @@ double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-HPRLP_results make_error_result(const char *status) {   // reference src/HPRLP.cu:66-79
-    HPRLP_results r;
-    std::memset(r.status, 0, sizeof(r.status));
-    std::strncpy(r.status, status, sizeof(r.status) - 1);
-    r.iter = 0; r.time = 0.0; r.primal_obj = 0.0; r.residuals = 0.0; r.gap = 0.0;
-    r.x = nullptr; r.y = nullptr; r.z = nullptr;
-    return r;
-}
+HPRLP_results make_error_result(const char *) { return hpr::abi_error_result(); }
 
 void print_banner_and_params(const HPRLP_parameters *p) {   // reference src/HPRLP.cu:15-46
     std::printf("\n==================================================================\n");
@@ -70,21 +64,12 @@ void prepare_engine(Engine &eng, const LP_info_cpu *lp, const HPRLP_parameters *
     if (!quiet) std::printf("Scaling time = %.2f seconds\n", hooks->scaling_seconds);
 }
 
-void fill_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info) {
-    if (!info) return;
-    info->lambda_max = h.lambda_max; info->sigma = h.sigma;
-    info->setup_seconds = h.setup_seconds; info->scaling_seconds = h.scaling_seconds; info->power_seconds = h.power_seconds;
-    info->loop_device_ms = h.loop_device_ms;
-    info->restarts = h.restarts; info->power_iters = h.power_iters; info->kernel_launches = h.kernel_launches;
-    info->b_scale = h.scal[0]; info->c_scale = h.scal[1]; info->norm_b = h.scal[2]; info->norm_c = h.scal[3];
-    info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
-    info->lanes_A = eng.A.G; info->lanes_AT = eng.AT.G; info->items_A = eng.A.n_items; info->items_AT = eng.AT.n_items;
-    info->bands_A = (int)eng.A.bands.size(); info->reserved0 = 0;
-}
+void fill_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info) { hpr::fill_b200_info(eng, h, info); }
 
 }  // namespace
 
 struct hprlp_b200_engine {
+    std::unique_ptr<hpr::Collective> coll;   // rank of a row-partitioned engine (declared first: destroyed after eng)
     Engine eng;
     HPRLP_parameters param;
     SolveHooks hooks;
@@ -97,9 +82,22 @@ HPRLP_results HPRLP_main_solve(const LP_info_cpu *lp, const HPRLP_parameters *pa
     return hprlp_b200_solve_ex(lp, param, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
 }
 
+static HPRLP_results solve_ex_impl(const LP_info_cpu *lp, const HPRLP_parameters *param_in, const double *power_z0,
+                                   int n_trace, const int *trace_iters, double *trace_x, double *trace_y,
+                                   double *trace_z, int quiet, hprlp_b200_info *info);
+
 HPRLP_results hprlp_b200_solve_ex(const LP_info_cpu *lp, const HPRLP_parameters *param_in, const double *power_z0,
                                   int n_trace, const int *trace_iters, double *trace_x, double *trace_y,
                                   double *trace_z, int quiet, hprlp_b200_info *info) {
+    // CUDA failures (out of memory, ...) become an "ERROR" result: nothing is thrown across the C ABI
+    return hpr::abi_guard_results("HPRLP_main_solve", [&] {
+        return solve_ex_impl(lp, param_in, power_z0, n_trace, trace_iters, trace_x, trace_y, trace_z, quiet, info);
+    });
+}
+
+static HPRLP_results solve_ex_impl(const LP_info_cpu *lp, const HPRLP_parameters *param_in, const double *power_z0,
+                                   int n_trace, const int *trace_iters, double *trace_x, double *trace_y,
+                                   double *trace_z, int quiet, hprlp_b200_info *info) {
     if (!lp || !lp->A) {
         std::cerr << "[error] Null model pointer" << std::endl;
         return make_error_result("ERROR");
@@ -132,6 +130,7 @@ HPRLP_results hprlp_b200_solve_ex(const LP_info_cpu *lp, const HPRLP_parameters 
 
 int hprlp_b200_power_start(int m, int device, double *out) {
     if (m <= 0 || !out) return -1;
+    return hpr::abi_guard_int("hprlp_b200_power_start", [&]() -> int {
     LP_info_cpu lp{};
     // minimal 1-nnz model just to own a stream/buffers of length m
     std::vector<int> rp((size_t)m + 1, 1); rp[0] = 0;
@@ -145,21 +144,51 @@ int hprlp_b200_power_start(int m, int device, double *out) {
     HPR_CUDA_CHECK(cudaMemcpyAsync(out, eng.wm, sizeof(double) * m, cudaMemcpyDeviceToHost, eng.stream));
     HPR_CUDA_CHECK(cudaStreamSynchronize(eng.stream));
     return 0;
+    });
 }
 
 hprlp_b200_engine *hprlp_b200_engine_create(const LP_info_cpu *lp, const HPRLP_parameters *param_in) {
     if (!lp || !lp->A) return nullptr;
-    HPRLP_parameters def;
-    auto *h = new hprlp_b200_engine;
-    h->param = param_in ? *param_in : def;
-    h->hooks.quiet = true;
-    prepare_engine(h->eng, lp, &h->param, &h->hooks, true);
-    h->eng.solve_begin(&h->param, &h->hooks);
-    return h;
+    return hpr::abi_guard<hprlp_b200_engine *>("hprlp_b200_engine_create", [&]() -> hprlp_b200_engine * {
+        HPRLP_parameters def;
+        std::unique_ptr<hprlp_b200_engine> h(new hprlp_b200_engine);   // released (engine, device memory) if setup throws
+        h->param = param_in ? *param_in : def;
+        h->hooks.quiet = true;
+        prepare_engine(h->eng, lp, &h->param, &h->hooks, true);
+        h->eng.solve_begin(&h->param, &h->hooks);
+        return h.release();
+    }, [] { return (hprlp_b200_engine *)nullptr; });
+}
+
+// Resident engine of ONE RANK of a row-partitioned solve (one process per GPU): this process uploads row block `rank`
+// of the model to device param->device_number; all ranks then call hprlp_b200_engine_run with the same arguments.
+hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *lp, const HPRLP_parameters *param_in, const char *uid128,
+                                                 int rank, int nranks) {
+    if (!lp || !lp->A || nranks < 1 || rank < 0 || rank >= nranks) return nullptr;
+    if (nranks == 1) return hprlp_b200_engine_create(lp, param_in);
+    if (!uid128 || nranks > lp->m) return nullptr;
+    return hpr::abi_guard<hprlp_b200_engine *>("hprlp_b200_engine_create_rank", [&]() -> hprlp_b200_engine * {
+        HPRLP_parameters def;
+        std::unique_ptr<hprlp_b200_engine> h(new hprlp_b200_engine);
+        h->param = param_in ? *param_in : def;
+        h->hooks.quiet = true;
+        h->coll.reset(hpr::open_nccl_rank(uid128, rank, nranks, h->param.device_number));
+        const std::vector<int> b = hpr::row_blocks_by_nnz(lp->A->rowPtr, lp->m, nranks);
+        h->eng.set_partition(h->coll.get(), lp->m, b[rank]);
+        const double t0 = now_seconds();
+        hpr::upload_row_block(h->eng, lp, b[rank], b[rank + 1], h->param.device_number);
+        h->hooks.setup_seconds = now_seconds() - t0;
+        const double t1 = now_seconds();
+        h->eng.scale(&h->param);
+        h->hooks.scaling_seconds = now_seconds() - t1;
+        h->eng.solve_begin(&h->param, &h->hooks);
+        return h.release();
+    }, [] { return (hprlp_b200_engine *)nullptr; });
 }
 
 double hprlp_b200_engine_run(hprlp_b200_engine *h, int iters) {
     if (!h || h->finished || iters <= 0) return 0.0;
+    return hpr::abi_guard_double("hprlp_b200_engine_run", [&]() -> double {
     Engine &e = h->eng;
     cudaEvent_t e0, e1;
     HPR_CUDA_CHECK(cudaEventCreate(&e0));
@@ -177,11 +206,12 @@ double hprlp_b200_engine_run(hprlp_b200_engine *h, int iters) {
         e.loop.output.x = e.loop.output.y = e.loop.output.z = nullptr;
     }
     return (double)ms;
+    });
 }
 
 double hprlp_b200_engine_time_phase(hprlp_b200_engine *h, int which, int reps) {
     if (!h || reps <= 0) return 0.0;
-    return h->eng.time_phase_ms(which, reps);
+    return hpr::abi_guard_double("hprlp_b200_engine_time_phase", [&]() -> double { return h->eng.time_phase_ms(which, reps); });
 }
 
 int hprlp_b200_engine_residuals(hprlp_b200_engine *h, double *kkt, double *pobj, double *dobj) {
@@ -201,10 +231,16 @@ void hprlp_b200_engine_info(hprlp_b200_engine *h, hprlp_b200_info *info) {
 
 void hprlp_b200_engine_destroy(hprlp_b200_engine *h) { delete h; }
 
+// Device memory cached by finished solves (the engines' private stream-ordered pool) goes back to the driver.
+void hprlp_b200_release_cached_memory(void) {
+    hpr::abi_guard_int("hprlp_b200_release_cached_memory", [&]() -> int { hpr::release_cached_device_memory(); return 0; });
+}
+
 int hprlp_b200_scale_only(const LP_info_cpu *lp, const HPRLP_parameters *param_in, double *A_val, int *AT_rowPtr,
                           int *AT_col, double *AT_val, double *AL, double *AU, double *l, double *u, double *c,
                           double *row_norm, double *col_norm, double *scalars6) {
     if (!lp || !lp->A) return -1;
+    return hpr::abi_guard_int("hprlp_b200_scale_only", [&]() -> int {
     HPRLP_parameters def;
     const HPRLP_parameters *param = param_in ? param_in : &def;
     Engine eng;
@@ -228,6 +264,7 @@ int hprlp_b200_scale_only(const LP_info_cpu *lp, const HPRLP_parameters *param_i
         scalars6[4] = eng.norm_b_org; scalars6[5] = eng.norm_c_org;
     }
     return 0;
+    });
 }
 
 void hprlp_b200_profiler_start(void) { cudaProfilerStart(); }
@@ -317,7 +354,7 @@ HPRLP_results solve(const LP_info_cpu *model, const HPRLP_parameters *param) {
     HPRLP_parameters default_param;
     const HPRLP_parameters *actual = param ? param : &default_param;
     if (!actual->use_presolve) return HPRLP_main_solve(model, actual);
-
+    return hpr::abi_guard_results("solve", [&]() -> HPRLP_results {
     LP_info_cpu reduced{};
     void *handle = nullptr;
     const bool presolve_ok = hpr::presolve_run(model, actual, &reduced, &handle);
@@ -329,6 +366,7 @@ HPRLP_results solve(const LP_info_cpu *model, const HPRLP_parameters *param) {
         hpr::free_lp_info_cpu(&reduced);
     }
     return result;
+    });
 }
 
 void free_model(LP_info_cpu *model) {

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/batched_solver.h"
+#include "abi_guard.h"
 #include "engine.h"
 #include "kernels.cuh"
 
@@ -795,6 +796,8 @@ extern "C" HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cp
     if (!model || !model->A || batch_size <= 0 || !C_in || !AL_in || !AU_in || !l_in || !u_in) {
         return make_batched_error("ERROR", model ? model->m : 0, model ? model->n : 0, std::max(batch_size, 0));
     }
+    // nothing is thrown across the C ABI: CUDA failures become "ERROR" status slots (reference :356-368 layout)
+    return abi_guard<HPRLP_batched_results>("solve_batched", [&]() -> HPRLP_batched_results {
     int avail = 0;
     if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) throw std::runtime_error("solve_batched: no CUDA device");
     HPRLP_parameters def;
@@ -853,6 +856,7 @@ extern "C" HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cp
     }
     out.time = out.setup_time + out.solve_time;
     return out;
+    }, [&] { return make_batched_error("ERROR", model->m, model->n, batch_size); });
 }
 
 // The reference entry point (src/batched_solver.cu:939).  HPRLP_NUM_GPUS=N (environment) shards the batch over N

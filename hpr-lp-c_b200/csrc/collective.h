@@ -1,0 +1,45 @@
+// collective.h -- the exchange steps of the row-partitioned mode: GPU p owns a row block of A and the
+// x-block J_p.  Per HPR iteration: reduce-scatter of the partial A_p^T y_p (every GPU ends up with the column sums of
+// ITS x-block), x-update on n/P entries, all-gather of the x_hat blocks; <= 9 residual scalars are all-reduced per
+// check.  Two transports behind one interface:
+//   * NCCL over NVLink 5 / NVSwitch (ncclReduceScatter / ncclAllGather / ncclAllReduce, in place), one communicator
+//     per GPU -- created with ncclCommInitAll (one host thread per GPU) or ncclCommInitRank (one process per GPU,
+//     unique id distributed by the caller, e.g. torch.distributed under torchrun);
+//   * "local": P logical ranks that can address each other's buffers directly (all on ONE device, or peer access
+//     enabled), synchronised by host barriers, reduced by plain kernels in rank order.  It exists so that the whole
+//     partitioned code path (row blocks, x-block ownership, every exchange) is parity-tested on a 1-GPU box:
+//     collectives of ranks that share a GPU must not wait on each other on the device (B200_PROFILING.md), so the
+//     waiting is done by the host threads.
+// The reference has no counterpart (single GPU, src/HPRLP.cu:51-64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "nccl_shim.h"
+
+namespace hpr {
+
+class Collective {
+   public:
+    int nranks = 1, rank = 0;
+    virtual ~Collective() {}
+    // in-place sum (or max) over ranks of buf[0..count)
+    virtual void all_reduce(double *buf, size_t count, bool max_op, cudaStream_t st) = 0;
+    // buf = nranks blocks of `block` doubles.  On return block `rank` holds the sum over ranks of that block
+    // (the other blocks are unspecified).
+    virtual void reduce_scatter_inplace(double *buf, size_t block, cudaStream_t st) = 0;
+    // buf = nranks blocks; block `rank` is this rank's contribution; on return every block is filled.
+    virtual void all_gather_inplace(double *buf, size_t block, cudaStream_t st) = 0;
+    // Unblocks peers stuck in a collective after this rank failed (ncclCommAbort / poisoned barrier).
+    virtual void abort() {}
+    virtual const char *name() const = 0;
+};
+
+Collective *make_nccl_collective(NcclComm comm, int nranks, int rank);   // takes ownership of the communicator
+
+struct LocalGroup;   // shared state of P in-process logical ranks
+LocalGroup *local_group_create(int nranks);
+void local_group_destroy(LocalGroup *g);
+Collective *make_local_collective(LocalGroup *g, int rank);
+
+}  // namespace hpr

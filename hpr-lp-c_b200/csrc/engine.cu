@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(kVecThreads) sumsq_kernel(const double *v, int
 
 // restart: movement norms |x_bar-x0|^2, |y_bar-y0|^2 (reference update_sigma axpby+nrm2,
 // src/main_iterate.cu:370-376) fused with do_restart's four copies (:312-322).
-__global__ void __launch_bounds__(kVecThreads) restart_kernel(const double *x_bar, double *x0, double *x, int n, const double *y_bar,
+__global__ void __launch_bounds__(kVecThreads) restart_kernel(const double *x_bar, double *x0, double *x, int j0, int j1, const double *y_bar,
                                                              double *y0, double *y, int m, double *partials) {
     double t[2] = {0.0, 0.0};
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += gridDim.x * blockDim.x) {
         const double xb = x_bar[j];
         const double d = xb - x0[j];
         t[0] += d * d;
@@ -190,17 +190,17 @@ __global__ void unscale_kernel(const double *x_bar, const double *z_bar, const d
     }
 }
 
-// ---- row-partitioned mode: unfused x-side kernels (the x-side is replicated on every GPU) -------------------
-// x-update from the all-reduced w = A^T y (same arithmetic as XPhaseOp::row)
+// ---- row-partitioned mode: unfused x-side kernels on the x-block [j0, j1) this GPU owns --------------------
+// x-update from the reduce-scattered w = (A^T y)_{J_p} (same arithmetic as XPhaseOp::row)
 template <bool CHECK>
 __global__ void __launch_bounds__(kVecThreads) x_update_kernel(const double *w, double *x, double *x_hat, const double *c, const double *l,
                                                               const double *u, const double *x0, double *x_bar, double *z_bar,
-                                                              double *x_tmp, const double *params, const int *kx, int *ky, int n) {
+                                                              double *x_tmp, const double *params, const int *kx, int *ky, int j0, int j1) {
     const double sigma = params[0];
     const int k = *kx;
     const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += gridDim.x * blockDim.x) {
         const double xi = x[j];
         const double zt = fma(sigma, w[j] - c[j], xi);
         const double xb = fmin(u[j], fmax(l[j], zt));
@@ -210,13 +210,13 @@ __global__ void __launch_bounds__(kVecThreads) x_update_kernel(const double *w, 
         if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
     }
 }
-// dual residual terms from the all-reduced w = A^T y_bar (same slots as ResidualDualOp)
+// dual residual terms from the reduce-scattered w = (A^T y_bar)_{J_p} (same slots as ResidualDualOp; sums over J_p)
 template <bool GAP, bool ITER0>
 __global__ void __launch_bounds__(kVecThreads) residual_dual_kernel(const double *w, const double *c, const double *z_bar, const double *x_bar,
                                                                    const double *x_tmp, const double *col_norm, const double *l,
-                                                                   const double *u, int n, double *partials) {
+                                                                   const double *u, int j0, int j1, double *partials) {
     double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += gridDim.x * blockDim.x) {
         const double cj = c[j], zb = z_bar[j], xb = x_bar[j], cn = col_norm[j];
         const double rd = (cj - w[j] - zb) * cn;
         t[0] += rd * rd; t[1] += cj * xb; t[2] += xb * zb;
@@ -258,7 +258,7 @@ static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
-    v.head_part = M.head_part; v.tail_part = M.tail_part;
+    v.head_part = M.head_part; v.tail_part = M.tail_part; v.ticket = M.ticket;
     v.carry_in = nullptr; v.carry_out = nullptr;
     return v;
 }
@@ -371,6 +371,33 @@ void pinned_block_release(double *p) {
     g_pinned_free.push_back(p);
 }
 
+// The engines' private stream-ordered pool, one per device, created on first use.
+namespace {
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
+}
+static cudaMemPool_t engine_pool(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (device < 0 || device >= 64) throw std::runtime_error("device number out of range");
+    if (!g_pools[device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        HPR_CUDA_CHECK(cudaMemPoolCreate(&g_pools[device], &props));
+        unsigned long long keep = 4096ULL << 20;
+        if (const char *e = getenv("HPRLP_POOL_RETAIN_MB")) keep = strtoull(e, nullptr, 10) << 20;
+        HPR_CUDA_CHECK(cudaMemPoolSetAttribute(g_pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    return g_pools[device];
+}
+void release_cached_device_memory() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (cudaMemPool_t p : g_pools)
+        if (p) HPR_CUDA_CHECK(cudaMemPoolTrimTo(p, 0));
+}
+
 static double now_seconds() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -409,12 +436,13 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.val = dalloc<double>(padded);
     const size_t witems = (size_t)M.n_items * kWarps;   // warp items (n_items = CTAs)
     M.item_row = dalloc<int>(witems + 1);
-    M.head_part = dalloc<PartSlot>(witems * 2);   // zero = "not published"; consumers clear what they read
+    M.head_part = dalloc<PartSlot>(witems * 2);   // all-ones = "not published" (set in finish_matrix); consumers re-arm what they read
     M.tail_part = dalloc<PartSlot>(witems * 2);
+    M.ticket = dalloc<unsigned>(2);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
-    dfree(M.head_part); dfree(M.tail_part);
+    dfree(M.head_part); dfree(M.tail_part); dfree(M.ticket);
     M = DevCsr();
 }
 
@@ -436,6 +464,10 @@ void Engine::finish_matrix(DevCsr &M) {
     const int entries = M.n_items * kWarps + 1;
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
+    const size_t part_bytes = sizeof(PartSlot) * (size_t)M.n_items * kWarps * 2;
+    HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0xFF, part_bytes, stream));   // every packet "not published"
+    HPR_CUDA_CHECK(cudaMemsetAsync(M.tail_part, 0xFF, part_bytes, stream));
+    HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, 2 * sizeof(unsigned), stream));
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
 }
 
@@ -457,7 +489,7 @@ void Engine::build_bands(DevCsr &M) {
     band_count(M.rows, M.rowPtr, M.col, (int)band_cols, nb, brp, bn.data(), stream);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t total = 0;
-    std::vector<size_t> o_col(nb), o_val(nb), o_item(nb), o_head(nb), o_tail(nb);
+    std::vector<size_t> o_col(nb), o_val(nb), o_item(nb), o_head(nb), o_tail(nb), o_tick(nb);
     std::vector<int> items(nb);
     for (int b = 0; b < nb; ++b) {
         items[b] = std::max(1, (int)((bn[b] + kChunk - 1) / kChunk));
@@ -467,12 +499,13 @@ void Engine::build_bands(DevCsr &M) {
         o_item[b] = total; total += up((wit + 1) * sizeof(int));
         o_head[b] = total; total += up(wit * 2 * sizeof(PartSlot));
         o_tail[b] = total; total += up(wit * 2 * sizeof(PartSlot));
+        o_tick[b] = total; total += up(2 * sizeof(unsigned));
     }
     const size_t o_carry = total; total += up((size_t)M.rows * sizeof(double));
     const size_t o_ptrs = total;  total += up(sizeof(void *) * 2 * nb);
     char *store = nullptr;
     HPR_CUDA_CHECK(cudaMalloc(&store, total));
-    HPR_CUDA_CHECK(cudaMemsetAsync(store, 0, total, stream));   // padding entries (col 0, value 0), packets "not published"
+    HPR_CUDA_CHECK(cudaMemsetAsync(store, 0, total, stream));   // padding entries (col 0, value 0); packets are armed by finish_matrix
     std::vector<void *> ptrs(2 * nb);
     M.bands.assign(nb, DevCsr());
     for (int b = 0; b < nb; ++b) {
@@ -484,6 +517,7 @@ void Engine::build_bands(DevCsr &M) {
         Bd.item_row = reinterpret_cast<int *>(store + o_item[b]);
         Bd.head_part = reinterpret_cast<PartSlot *>(store + o_head[b]);
         Bd.tail_part = reinterpret_cast<PartSlot *>(store + o_tail[b]);
+        Bd.ticket = reinterpret_cast<unsigned *>(store + o_tick[b]);
         ptrs[b] = Bd.col; ptrs[nb + b] = Bd.val;
     }
     HPR_CUDA_CHECK(cudaMemcpyAsync(store + o_ptrs, ptrs.data(), sizeof(void *) * 2 * nb, cudaMemcpyHostToDevice, stream));
@@ -501,8 +535,9 @@ void Engine::build_bands(DevCsr &M) {
 }
 
 void Engine::alloc_common() {
-    x = dalloc<double>(n); x0 = dalloc<double>(n); x_hat = dalloc<double>(n); x_bar = dalloc<double>(n);
-    z_bar = dalloc<double>(n); x_tmp = dalloc<double>(n); wn = dalloc<double>(n);
+    const size_t nv = dist() ? npad : (size_t)n;   // partitioned: exchange buffers hold nranks equal blocks
+    x = dalloc<double>(nv); x0 = dalloc<double>(nv); x_hat = dalloc<double>(nv); x_bar = dalloc<double>(nv);
+    z_bar = dalloc<double>(nv); x_tmp = dalloc<double>(nv); wn = dalloc<double>(nv);
     y = dalloc<double>(m); y0 = dalloc<double>(m); y_bar = dalloc<double>(m); y_obj = dalloc<double>(m);
     y_tmp = dalloc<double>(m); wm = dalloc<double>(m); wm2 = dalloc<double>(m);
     row_norm = dalloc<double>(m); col_norm = dalloc<double>(n);
@@ -618,28 +653,34 @@ void Engine::prepare(int m_, int n_, long long nnz_, int dev) {
     HPR_CUDA_CHECK(cudaSetDevice(device));
     HPR_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     m = m_; n = n_; nnz = nnz_;
+    if (dist()) {   // x-block ownership: equal blocks of xblock columns (multiple of 64 entries = 512 B), the last one short
+        xblock = (((size_t)n + nranks - 1) / nranks + 63) / 64 * 64;
+        npad = xblock * nranks;
+        xb0 = (int)std::min<size_t>((size_t)n, xblock * rank);
+        xb1 = (int)std::min<size_t>((size_t)n, xblock * (rank + 1));
+    } else {
+        xblock = npad = (size_t)n; xb0 = 0; xb1 = n;
+    }
     {
         // arena size: two padded CSR copies + item tables + 5 problem vectors + 9 n-vectors + 8 m-vectors + partials
         const size_t ctas = (size_t)((nnz + kChunk - 1) / kChunk) + 1, padded = ctas * kChunk, witems = ctas * kWarps;
         size_t need = 0;
         for (size_t rows : {(size_t)m, (size_t)n})
             need += arena_round((rows + 1) * 4) + arena_round(padded * 4) + arena_round(padded * 8) + arena_round((witems + 1) * 4) +
-                    2 * arena_round(witems * 2 * sizeof(PartSlot));
-        need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((size_t)n * 8);
+                    2 * arena_round(witems * 2 * sizeof(PartSlot)) + arena_round(8);
+        need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((dist() ? npad : (size_t)n) * 8);
         need += arena_round((size_t)(ctas + witems / kWarps + kVecBlocks + 64) * kMaxSlots * 8) + (1u << 16);
         Arena *ar = new Arena;
         ar->size = need;
-        // Stream-ordered allocation from the device's default memory pool with an unlimited release threshold: the
-        // arena of a finished solve stays cached in the pool, so repeated solve() calls pay neither cudaMalloc nor
-        // cudaFree (both synchronous and ~0.1-0.5 s for multi-GB buffers).  HPRLP_NO_POOL=1 restores cudaMalloc/cudaFree.
+        // Stream-ordered allocation from a PRIVATE memory pool per device (the process's default pool is left alone): the
+        // arena of a finished solve stays cached up to the pool's release threshold, so repeated solve() calls pay neither
+        // cudaMalloc nor cudaFree (both synchronous and ~0.1-0.5 s for multi-GB buffers).  HPRLP_POOL_RETAIN_MB bounds what
+        // stays cached (default 4096 MB; 0 = return everything as soon as an engine is destroyed);
+        // hprlp_b200_release_cached_memory() returns it all on demand.  HPRLP_NO_POOL=1 restores cudaMalloc/cudaFree.
         static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
         pooled_ = !no_pool;
         if (pooled_) {
-            cudaMemPool_t pool = nullptr;
-            HPR_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-            unsigned long long keep = ~0ULL;
-            HPR_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&ar->base), need, stream));
+            HPR_CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ar->base), need, engine_pool(device), stream));
         } else {
             HPR_CUDA_CHECK(cudaMalloc(&ar->base, need));
         }
@@ -658,7 +699,7 @@ void Engine::finish_setup(bool build_transpose) {
     finish_matrix(A);
     finish_matrix(AT);
     alloc_common();
-    zo_buf = dalloc<double>(n);
+    zo_buf = dalloc<double>(dist() ? npad : (size_t)n);
     g_arena = nullptr;
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
@@ -705,12 +746,17 @@ Engine::~Engine() {
                 t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
 }
 
+void Engine::set_partition(Collective *c, int m_global_, int row0_) {
+    coll = c;
+    nranks = c ? c->nranks : 1;
+    rank = c ? c->rank : 0;
+    m_global = m_global_;
+    row0 = row0_;
+}
+
 void Engine::allreduce(double *buf, size_t count, bool max_op) {
-    if (!comm) return;
-    static const bool skip = getenv("HPRLP_DEBUG_SKIP_ALLREDUCE") != nullptr;   // timing experiments only (wrong results)
-    if (skip) return;
-    const int rc = nccl().AllReduce(buf, buf, count, kNcclFloat64, max_op ? kNcclMax : kNcclSum, comm, stream);
-    if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce failed: ") + nccl().GetErrorString(rc));
+    if (!coll) return;
+    coll->all_reduce(buf, count, max_op, stream);
 }
 
 void Engine::fetch_scalars(int count) {
@@ -917,7 +963,7 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
 // iteration building blocks
 // ------------------------------------------------------------------------------------------------
 void Engine::init_iterates() {
-    for (double *v : {x, x0, x_hat, x_bar, z_bar, x_tmp}) HPR_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, stream));
+    for (double *v : {x, x0, x_hat, x_bar, z_bar, x_tmp}) HPR_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * (dist() ? npad : (size_t)n), stream));
     for (double *v : {y, y0, y_bar, y_obj, y_tmp}) HPR_CUDA_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * m, stream));
     reset_halpern_counter();
     upload_params();
@@ -932,19 +978,23 @@ void Engine::reset_halpern_counter() { HPR_CUDA_CHECK(cudaMemsetAsync(d_k, 0, 2 
 
 void Engine::launch_iteration(bool check) {
     if (dist()) {
-        // Row-partitioned x-phase: partial w_p = A_p^T y_p, NCCL all-reduce over the row blocks (NVLink), then the
-        // replicated x-update; the y-phase stays fused (local rows of A, full x_hat).  SURVEY.md 8e.
-        SpmvOp<false> ow; ow.g = y; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
-        launch_stream(AT, ow, stream);
-        allreduce(wn, n);
+        // Row-partitioned iteration: partial w_p = A_p^T y_p over the local rows, reduce-scatter so that this
+        // GPU holds (A^T y) on ITS x-block, x-update on that block only, all-gather of the x_hat blocks, then the fused
+        // y-phase on the local rows of A with the full x_hat.
+        SpmvOp<false, true> ow; ow.g = y; ow.tex = tex_y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+        launch_stream_hot(AT, ow, stream);
+        coll->reduce_scatter_inplace(wn, xblock, stream);
+        const int gx = vec_grid(xb1 - xb0);
         if (check) {
-            x_update_kernel<true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, n);
+            x_update_kernel<true><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, xb0, xb1);
+            coll->all_gather_inplace(x_hat, xblock, stream);
             YPhaseOp<true> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         } else {
-            x_update_kernel<false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, n);
+            x_update_kernel<false><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+            coll->all_gather_inplace(x_hat, xblock, stream);
             YPhaseOp<false> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
@@ -1024,11 +1074,14 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     if (dist()) {
         SpmvOp<false> ow; ow.g = y_bar; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
         launch_stream(AT, ow, stream);
-        allreduce(wn, n);
-        if (iter == 0) residual_dual_kernel<false, true><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
-        else if (compute_gap) residual_dual_kernel<true, false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
-        else residual_dual_kernel<false, false><<<kVecBlocks, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, n, d_partials);
-        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 5, d_scal);   // x-side sums are replicated: no reduce
+        coll->reduce_scatter_inplace(wn, xblock, stream);
+        const int gx = vec_grid(xb1 - xb0);
+        if (iter == 0) residual_dual_kernel<false, true><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        else if (compute_gap) residual_dual_kernel<true, false><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        else residual_dual_kernel<false, false><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, gx, 5, d_scal);   // sums over the owned x-block: all-reduced below
+        coll->all_gather_inplace(x_bar, xblock, stream);                          // the primal pass gathers the full x_bar
+        if (compute_gap) coll->all_gather_inplace(x_tmp, xblock, stream);
     } else {
     if (iter == 0) { ResidualDualOp<false, true> o; fill_dual(o); launch_stream(AT, o, stream); }
     else if (compute_gap) { ResidualDualOp<true, false> o; fill_dual(o); launch_stream(AT, o, stream); }
@@ -1053,7 +1106,8 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal + 7);
         launches += 2;
     }
-    allreduce(d_scal + 5, 4);   // y-side sums are partial per row block
+    if (dist() && !compute_gap) HPR_CUDA_CHECK(cudaMemsetAsync(d_scal + 7, 0, 2 * sizeof(double), stream));
+    allreduce(d_scal, 9);   // x-side sums are partial per x-block, y-side sums per row block
     if (timing) cudaEventRecord(te1, stream);
     fetch_scalars(9);
     HPR_CUDA_CHECK(cudaGetLastError());
@@ -1095,12 +1149,13 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
 
 // reference compute_weighted_norm, src/main_iterate.cu:486-515
 double Engine::weighted_norm_after_restart() {
+    if (dist()) coll->all_gather_inplace(x_tmp, xblock, stream);   // A dx needs every block of dx
     WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
     launch_stream(A, o, stream);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
-    allreduce(d_scal, 2);
-    sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp, n, d_partials);
+    sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp + xb0, xb1 - xb0, d_partials);   // |dx|^2 over the owned block
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
+    allreduce(d_scal, 3);
     launches += 4;
     fetch_scalars(3);
     const double dot_prod = 2.0 * h_scal[0];
@@ -1120,10 +1175,10 @@ double Engine::weighted_norm_after_restart() {
 // reference update_sigma + do_restart + upload_halpern_restart_params,
 // src/main_iterate.cu:367-404, 312-322, 54-66
 void Engine::restart_and_sigma(RestartState *rs, const Residuals &res) {
-    restart_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_bar, x0, x, n, y_bar, y0, y, m, d_partials);
+    restart_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_bar, x0, x, xb0, xb1, y_bar, y0, y, m, d_partials);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 2, d_scal);
     launches += 2;
-    allreduce(d_scal + 1, 1);   // |y_bar - y0|^2 is partial per row block, |x_bar - x0|^2 replicated
+    allreduce(d_scal, 2);   // |x_bar - x0|^2 is partial per x-block, |y_bar - y0|^2 per row block
     fetch_scalars(2);
     const double primal_move = sqrt(h_scal[0]);
     const double dual_move = sqrt(h_scal[1]);
@@ -1158,13 +1213,29 @@ void Engine::collect_solution(double *hx, double *hy, double *hz) {
     // unscale into scratch (wn, x_hat reused as z scratch is NOT allowed: x_hat is live) -> use wn/wm + x_tmp copy
     double *xo = wn, *yo = wm;
     double *zo = zo_buf;
+    if (dist()) {   // every GPU owns one block of x_bar / z_bar
+        coll->all_gather_inplace(x_bar, xblock, stream);
+        coll->all_gather_inplace(z_bar, xblock, stream);
+    }
     unscale_kernel<<<vec_grid(std::max(m, n)), kVecThreads, 0, stream>>>(x_bar, z_bar, col_norm, xo, zo, n, y_bar, row_norm, yo, m,
                                                                          b_scale, c_scale);
     launches++;
     HPR_CUDA_CHECK(cudaMemcpyAsync(hx, xo, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
-    HPR_CUDA_CHECK(cudaMemcpyAsync(hy, yo, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
     HPR_CUDA_CHECK(cudaMemcpyAsync(hz, zo, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+    if (!dist()) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(hy, yo, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return;
+    }
+    // y of the whole problem on every rank: the row blocks are placed in a zeroed m_global-vector and summed
+    double *yfull = nullptr;
+    HPR_CUDA_CHECK(cudaMalloc(&yfull, sizeof(double) * (size_t)m_global));
+    HPR_CUDA_CHECK(cudaMemsetAsync(yfull, 0, sizeof(double) * (size_t)m_global, stream));
+    HPR_CUDA_CHECK(cudaMemcpyAsync(yfull + row0, yo, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+    allreduce(yfull, (size_t)m_global);
+    HPR_CUDA_CHECK(cudaMemcpyAsync(hy, yfull, sizeof(double) * (size_t)m_global, cudaMemcpyDeviceToHost, stream));
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(yfull);
 }
 
 double Engine::time_phase_ms(int which, int reps) {
@@ -1177,6 +1248,13 @@ double Engine::time_phase_ms(int which, int reps) {
             ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
             ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
             launch_stream_hot(AT, ox, stream);
+        } else if (which == 2) {   // row-partitioned x-side pass: partial w_p = A_p^T y_p
+            SpmvOp<false, true> ow; ow.g = y; ow.tex = tex_y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+            launch_stream_hot(AT, ow, stream);
+        } else if (which == 3) {   // row-partitioned x-update on the owned block (from whatever wn holds)
+            x_update_kernel<false><<<vec_grid(xb1 - xb0), kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+        } else if (which == 4) {   // the two exchanges of one iteration, as the loop issues them
+            if (coll) { coll->reduce_scatter_inplace(wn, xblock, stream); coll->all_gather_inplace(x_hat, xblock, stream); }
         } else {
             YPhaseOp<false> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
@@ -1324,7 +1402,7 @@ bool Engine::solve_advance(const HPRLP_parameters *param, SolveHooks *hooks, int
             output.iter6 = (output.iter6 == 0) ? output.iter : output.iter6;
             output.iter8 = (output.iter8 == 0) ? output.iter : output.iter8;
             output.x = static_cast<double *>(std::malloc(sizeof(double) * n));
-            output.y = static_cast<double *>(std::malloc(sizeof(double) * m));
+            output.y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)mg()));
             output.z = static_cast<double *>(std::malloc(sizeof(double) * n));
             collect_solution(output.x, output.y, output.z);
             if (!quiet) {
@@ -1376,7 +1454,7 @@ bool Engine::solve_advance(const HPRLP_parameters *param, SolveHooks *hooks, int
 
         for (int t = 0; t < hooks->n_trace; ++t) {
             if (hooks->trace_iters[t] == iter && (last_is_check || (restart && count == 1))) {
-                collect_solution(hooks->trace_x + (size_t)t * n, hooks->trace_y + (size_t)t * m, hooks->trace_z + (size_t)t * n);
+                collect_solution(hooks->trace_x + (size_t)t * n, hooks->trace_y + (size_t)t * mg(), hooks->trace_z + (size_t)t * n);
             }
         }
     }

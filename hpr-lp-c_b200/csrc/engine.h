@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "../../include/structs.h"
+#include "../../include/hprlp_b200.h"
+#include "collective.h"
 #include "nccl_shim.h"
 
 namespace hpr {
@@ -27,7 +29,7 @@ namespace hpr {
 
 #ifndef HPR_PARTSLOT_DEFINED
 #define HPR_PARTSLOT_DEFINED
-struct alignas(16) PartSlot { double v; unsigned long long ready; };   // one published partial sum (kernels.cuh)
+typedef unsigned long long PartSlot;   // one published partial sum (kernels.cuh): bits of the double, ~0 = not published
 #endif
 
 // Device CSR matrix + the item decomposition used by csr_stream_kernel.
@@ -39,7 +41,8 @@ struct DevCsr {
     double *val = nullptr;  // padded likewise
     int *item_row = nullptr;
     int n_items = 0;
-    PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries
+    PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries (all-ones = empty)
+    unsigned *ticket = nullptr;   // [2] chunk ticket + finished-CTA counter of csr_stream_kernel (zero between launches)
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
@@ -137,11 +140,19 @@ class Engine {
     long long nnz = 0;
     int device = 0;
     // Row-block partition over several GPUs: this engine owns rows [row0, row0+m) of a global
-    // m_global x n problem; x-side vectors are replicated, y-side vectors are local.  comm == nullptr: single GPU.
-    NcclComm comm = nullptr;
+    // m_global x n problem -- A_p, A_p^T, the y-side vectors of those rows -- and the x-block J_p = [xb0, xb1) of
+    // columns: the x-update, the x-side residual terms and the movement norms run on J_p only.  Per iteration:
+    // partial A_p^T y_p -> reduce-scatter -> x-update on J_p -> all-gather of x_hat -> fused y-phase on the local rows.
+    // n-vectors are allocated with npad = nranks * xblock entries so both exchanges run in place.
+    // coll == nullptr: single GPU.
+    Collective *coll = nullptr;
     int nranks = 1, rank = 0, m_global = 0, row0 = 0;
-    bool dist() const { return comm != nullptr; }
+    int xb0 = 0, xb1 = 0;          // owned columns
+    size_t xblock = 0, npad = 0;   // exchange block (multiple of 64 entries), padded n-vector length
+    bool dist() const { return coll != nullptr; }
+    void set_partition(Collective *c, int m_global_, int row0_);   // before upload()/prepare()
     void allreduce(double *buf, size_t count, bool max_op = false);
+    int mg() const { return dist() ? m_global : m; }   // length of the y returned by collect_solution
     DevCsr A, AT;
     double *AL = nullptr, *AU = nullptr, *c = nullptr, *l = nullptr, *u = nullptr;
     double *row_norm = nullptr, *col_norm = nullptr;
@@ -193,6 +204,15 @@ void band_fill(int rows, const int *d_rowPtr, const int *d_col, const double *d_
 
 void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, const int *d_col, const double *d_val,
                           int *d_trp, int *d_tcol, double *d_tval, cudaStream_t st);
+
+// row-partitioned mode (partitioned.cu)
+std::vector<int> row_blocks_by_nnz(const int *rowPtr, int m, int P);
+void upload_row_block(Engine &eng, const LP_info_cpu *model, int r0, int r1, int device);
+Collective *open_nccl_rank(const char *uid128, int rank, int nranks, int device);
+void fill_b200_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info);
+
+// device memory pool of the engines (engine.cu)
+void release_cached_device_memory();
 
 // presolve bridge (presolve.cpp); returns false when unavailable / failed (caller solves the original model)
 bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);

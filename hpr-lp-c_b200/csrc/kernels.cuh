@@ -18,11 +18,14 @@
 //           epilogue (projection, dual update, Halpern averaging, residual terms ...) runs
 //           lane-parallel over consecutive rows with coalesced vector loads/stores.
 //   rows cut by an item boundary: every item but the last one of the row publishes its partial sum as one
-//           16-byte {value, ready} packet; the warp whose item holds the END of the row waits for the packets of
-//           the items to its left (they belong to lower-numbered warps of the same CTA or to lower-numbered,
-//           i.e. earlier dispatched, CTAs: the in-order "look-back" used by single-pass scans), adds them in item
-//           order, runs the epilogue and clears the packets for the next launch.  No second launch, no atomics,
-//           no fences, and the summation order is fixed, so results are bitwise run-to-run reproducible.
+//           8-byte packet (an aligned 64-bit relaxed store: single-copy atomic, so the value IS the ready flag --
+//           an all-ones NaN pattern that no arithmetic produces means "not published"); the warp whose item
+//           holds the END of the row waits for the packets of the items to its left, adds them in item order,
+//           runs the epilogue and re-arms the packets for the next launch.  A CTA takes the chunk it works on
+//           from an atomic ticket (not from blockIdx), so the items to the left always belong to CTAs that
+//           STARTED earlier: the decoupled look-back of single-pass scans, deadlock-free under any dispatch
+//           order, preemption or residency.  No second launch, no fences, and the summation order is fixed by the
+//           item order, so results are bitwise run-to-run reproducible.
 //
 // Replaces, on the iteration path, the reference's fused_update_* kernels
 // (src/cuda_kernels/HPR_cuda_kernels.cu:297-427), its cuSPARSE SpMV + elementwise kernels
@@ -58,8 +61,9 @@ constexpr int kSeqPartials = 8;                 // split rows with more partials
 
 #ifndef HPR_PARTSLOT_DEFINED
 #define HPR_PARTSLOT_DEFINED
-struct alignas(16) PartSlot { double v; unsigned long long ready; };   // one published partial sum (see part_publish)
+typedef unsigned long long PartSlot;   // one published partial sum: the bits of the double, kPartEmpty = not published
 #endif
+constexpr unsigned long long kPartEmpty = ~0ULL;   // a NaN payload no fp64 instruction generates (canonical NaN = 0xfff8...)
 
 template <typename RP>
 struct CsrView {
@@ -72,6 +76,7 @@ struct CsrView {
     int n_items;          // CTAs in the grid
     PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
     PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
+    unsigned *ticket;     // [2]: {next chunk to hand out, CTAs finished}; both zero between launches
     // Column-banded matrices (engine.cu, build_bands): a pass over the matrix is one launch per band; every band but the
     // last stores its row sums (+ those of the bands before it) in carry_out instead of running the epilogue, the last
     // band adds carry_in to its own row sums first.  Both null for an ordinary matrix.  Single-product ops only.
@@ -79,34 +84,42 @@ struct CsrView {
     double *carry_out;
 };
 
-// Publish / consume one partial sum.  Value and ready flag travel in ONE aligned 16-byte access, so no fence is needed
-// between them; the consumer clears the packet (all packets are zero between launches).
+// Publish / consume one partial sum.  The packet is ONE aligned 64-bit word: value and "ready" cannot be torn and
+// no fence is needed (nothing else is communicated through memory).  The consumer re-arms the packet.
+__device__ __forceinline__ unsigned long long part_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b == kPartEmpty ? 0xfff8000000000000ULL : b;   // (unreachable for computed values; keeps the protocol total)
+}
 __device__ __forceinline__ void part_publish(PartSlot *p, double v) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(1ll) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(part_bits(v)) : "memory");
 }
 __device__ __forceinline__ double part_consume(PartSlot *p) {
-    long long a, f;
+    unsigned long long a;
+    unsigned spins = 0;
     for (;;) {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(f) : "l"(p) : "memory");
-        if (f != 0) break;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+        if (a != kPartEmpty) break;
         __nanosleep(64);   // every poll is a request on the L1->crossbar port, the unit that bounds this kernel
+        if (++spins > (1u << 28)) __trap();   // > 15 s: a protocol bug must kill the context, not hang the GPU
     }
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %1};" ::"l"(p), "l"(0ll) : "memory");
-    return __longlong_as_double(a);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(kPartEmpty) : "memory");
+    return __longlong_as_double((long long)a);
 }
 // The same hand-off between two warps of one CTA goes through shared memory (7 of 8 cut rows): no L2 round trip.
 __device__ __forceinline__ void part_publish_cta(PartSlot *p, double v) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(a), "l"(__double_as_longlong(v)), "l"(1ll) : "memory");
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(a), "l"(part_bits(v)) : "memory");
 }
 __device__ __forceinline__ double part_consume_cta(PartSlot *p) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(p);
-    long long a, f;
+    unsigned long long a;
+    unsigned spins = 0;
     do {
-        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(f) : "r"(s) : "memory");
-    } while (f == 0);
-    asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %1};" ::"r"(s), "l"(0ll) : "memory");
-    return __longlong_as_double(a);
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(a) : "r"(s) : "memory");
+        if (++spins > (1u << 30)) __trap();
+    } while (a == kPartEmpty);
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(s), "l"(kPartEmpty) : "memory");
+    return __longlong_as_double((long long)a);
 }
 
 __device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
@@ -165,8 +178,14 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     double *red_scratch = smem + (size_t)kWarps * NV * kWarpChunk;
     __shared__ double own_part[kWarps * 2];     // [warp][2]: this item's share of the row it finishes
     __shared__ PartSlot cta_part[kWarps * 4];   // [warp][head, tail][2]: partials handed to a warp of this CTA
-    if (threadIdx.x < kWarps * 4) { cta_part[threadIdx.x].v = 0.0; cta_part[threadIdx.x].ready = 0ull; }
+    __shared__ unsigned chunk_s;
+    // The chunk this CTA works on comes from a ticket: chunks are handed out in the order CTAs START, so every item to
+    // the left of ours belongs to a CTA that is already running (or done) -- the look-back below cannot wait for a CTA
+    // that was never scheduled, whatever order the hardware dispatches blockIdx in.
+    if (threadIdx.x == 0) chunk_s = atomicAdd(M.ticket, 1u);
+    if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
+    const int chunk = (int)chunk_s;
 
     op.init();
     auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
@@ -174,9 +193,9 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
         if (M.carry_out) M.carry_out[r] = t[0];
         else op.row(r, t, q0, q1);
     };
-    const int item = blockIdx.x * kWarps + warp;
-    const int cta_item0 = blockIdx.x * kWarps;
-    const long long cta_end = ((long long)blockIdx.x + 1) * kChunk;   // a row with p1 <= cta_end ends inside this CTA
+    const int item = chunk * kWarps + warp;
+    const int cta_item0 = chunk * kWarps;
+    const long long cta_end = ((long long)chunk + 1) * kChunk;   // a row with p1 <= cta_end ends inside this CTA
     const long long s = (long long)item * kWarpChunk;
     const long long e = (s + kWarpChunk < M.nnz) ? s + kWarpChunk : (s < M.nnz ? M.nnz : s);
 
@@ -333,7 +352,12 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
         }
         if (lane == 0) complete_row(rA, sum, P0, P1);
     }
-    if (!M.carry_out) op.finish(red_scratch, blockIdx.x);   // (warp-uniform: kernel argument)
+    if (!M.carry_out) op.finish(red_scratch, chunk);   // (warp-uniform: kernel argument); partials indexed by chunk: deterministic
+    // the last CTA to finish re-arms the ticket for the next launch over this matrix (launches are stream-ordered)
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(M.ticket + 1, 1u);
+        if (done == gridDim.x - 1) { M.ticket[0] = 0u; M.ticket[1] = 0u; }
+    }
 }
 
 // item_row[i] = first row finalised by warp item i = first r with rowPtr[r+1] > i*kWarpChunk (item 0 also owns

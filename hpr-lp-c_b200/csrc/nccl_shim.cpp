@@ -25,6 +25,9 @@ const NcclApi &nccl() {
         api.CommInitRank = reinterpret_cast<int (*)(NcclComm *, int, NcclUniqueId, int)>(sym("ncclCommInitRank"));
         api.CommInitAll = reinterpret_cast<int (*)(NcclComm *, int, const int *)>(sym("ncclCommInitAll"));
         api.CommDestroy = reinterpret_cast<int (*)(NcclComm)>(sym("ncclCommDestroy"));
+        api.CommAbort = reinterpret_cast<int (*)(NcclComm)>(sym("ncclCommAbort"));
+        api.ReduceScatter = reinterpret_cast<int (*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t)>(sym("ncclReduceScatter"));
+        api.AllGather = reinterpret_cast<int (*)(const void *, void *, size_t, int, NcclComm, cudaStream_t)>(sym("ncclAllGather"));
         api.AllReduce = reinterpret_cast<int (*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t)>(sym("ncclAllReduce"));
         api.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
         api.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));

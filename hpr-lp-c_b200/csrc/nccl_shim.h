@@ -15,6 +15,9 @@ struct NcclApi {
     int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
     int (*CommInitAll)(NcclComm *, int, const int *) = nullptr;
     int (*CommDestroy)(NcclComm) = nullptr;
+    int (*CommAbort)(NcclComm) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t /*recvcount*/, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t /*sendcount*/, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int /*dtype*/, int /*op*/, NcclComm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;

@@ -5,7 +5,9 @@
 // row with duplicates re-drawn; values U(-1,1) with |v| >= 1e-3), so a block generated here is bit-identical to the
 // host generator's rows (tests/test_gpu_partitioned.py checks it).  Test/bench infrastructure that lives in the
 // library only because it must write straight into engine buffers.
+#include <chrono>
 #include <cmath>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -14,7 +16,9 @@
 
 #include "../../include/HPRLP.h"
 #include "../../include/hprlp_b200.h"
+#include "abi_guard.h"
 #include "engine.h"
+#include "rank_group.h"
 
 namespace hpr {
 namespace {
@@ -136,116 +140,130 @@ using namespace hpr;
 
 // Debug/test hook: rows [row0, row0+rows) of the synthetic uniform matrix generated on the device, copied to the host.
 extern "C" int hprlp_b200_synth_rows(int n, int K, unsigned long long seed, long long row0, int rows, int *col_out, double *val_out) {
-    if (rows <= 0 || K <= 0 || K > 4096 || K > n) return -1;
-    int *rp = nullptr, *col = nullptr;
-    double *val = nullptr;
-    HPR_CUDA_CHECK(cudaMalloc(&rp, sizeof(int) * ((size_t)rows + 1)));
-    HPR_CUDA_CHECK(cudaMalloc(&col, sizeof(int) * (size_t)rows * K));
-    HPR_CUDA_CHECK(cudaMalloc(&val, sizeof(double) * (size_t)rows * K));
-    generate_rows(rows, row0, K, n, seed, rp, col, val, 0);
-    HPR_CUDA_CHECK(cudaMemcpy(col_out, col, sizeof(int) * (size_t)rows * K, cudaMemcpyDeviceToHost));
-    HPR_CUDA_CHECK(cudaMemcpy(val_out, val, sizeof(double) * (size_t)rows * K, cudaMemcpyDeviceToHost));
-    cudaFree(rp); cudaFree(col); cudaFree(val);
-    return 0;
+    return abi_guard_int("hprlp_b200_synth_rows", [&]() -> int {
+        if (rows <= 0 || K <= 0 || K > 4096 || K > n) return -1;
+        int *rp = nullptr, *col = nullptr;
+        double *val = nullptr;
+        HPR_CUDA_CHECK(cudaMalloc(&rp, sizeof(int) * ((size_t)rows + 1)));
+        HPR_CUDA_CHECK(cudaMalloc(&col, sizeof(int) * (size_t)rows * K));
+        HPR_CUDA_CHECK(cudaMalloc(&val, sizeof(double) * (size_t)rows * K));
+        generate_rows(rows, row0, K, n, seed, rp, col, val, 0);
+        HPR_CUDA_CHECK(cudaMemcpy(col_out, col, sizeof(int) * (size_t)rows * K, cudaMemcpyDeviceToHost));
+        HPR_CUDA_CHECK(cudaMemcpy(val_out, val, sizeof(double) * (size_t)rows * K, cudaMemcpyDeviceToHost));
+        cudaFree(rp); cudaFree(col); cudaFree(val);
+        return 0;
+    });
 }
+
+namespace {
+
+struct SynthSpec { long long m; int n, K; unsigned long long seed; };
+
+void check_synth(const SynthSpec &s, int P) {
+    if (s.m <= 0 || s.n <= 0 || s.K <= 0 || s.K > s.n || s.K > 4096 || s.m > 2147483647LL) throw std::runtime_error("synth: bad dimensions");
+    if ((s.m + P - 1) / P * (long long)s.K >= 2147483647LL) throw std::runtime_error("synth: a shard would exceed 2^31 nonzeros; use more GPUs");
+}
+
+// One rank: generate rows [m p/P, m (p+1)/P) and the vectors on the device, scale, solve.  coll == nullptr: single GPU.
+HPRLP_results synth_rank(const SynthSpec &sp, int p, int P, int device, Collective *coll, const HPRLP_parameters &param, bool quiet,
+                         double *obj_out, hprlp_b200_info *info) {
+    const long long r0 = sp.m * p / P, r1 = sp.m * (p + 1) / P;
+    const int mp = (int)(r1 - r0), n = sp.n, K = sp.K;
+    const long long nnzp = (long long)mp * K;
+    HPRLP_parameters pp = param;
+    pp.device_number = device;
+    Engine eng;
+    if (coll) eng.set_partition(coll, (int)sp.m, (int)r0);
+    SolveHooks hooks;
+    hooks.quiet = quiet;
+    const auto t0 = std::chrono::steady_clock::now();
+    eng.prepare(mp, n, nnzp, device);
+    generate_rows(mp, r0, K, n, sp.seed, eng.A.rowPtr, eng.A.col, eng.A.val, eng.stream);
+    eng.finish_setup(true);
+    // vectors: x*, z* live in x_bar / z_bar until init_iterates() clears them
+    double *xs = eng.x_bar, *zs = eng.z_bar, *ys = eng.wm2, *ax = eng.wm, *w = eng.wn;
+    gen_col_vectors_kernel<<<1184, 256, 0, eng.stream>>>(n, sp.seed, sp.seed, eng.l, eng.u, xs, zs);
+    eng.spmv_A(xs, ax);
+    gen_row_vectors_kernel<<<1184, 256, 0, eng.stream>>>(mp, r0, sp.seed, sp.seed, ax, eng.AL, eng.AU, ys);
+    eng.spmv_AT(ys, w);
+    eng.allreduce(w, (size_t)n);
+    HPR_CUDA_CHECK(cudaMemsetAsync(eng.d_scal, 0, sizeof(double), eng.stream));
+    gen_cost_kernel<<<1184, 256, 0, eng.stream>>>(n, w, zs, xs, eng.c, eng.d_scal);
+    double obj = 0.0;
+    HPR_CUDA_CHECK(cudaMemcpyAsync(&obj, eng.d_scal, sizeof(double), cudaMemcpyDeviceToHost, eng.stream));
+    HPR_CUDA_CHECK(cudaStreamSynchronize(eng.stream));
+    if (obj_out) *obj_out = obj;
+    hooks.setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const auto t1 = std::chrono::steady_clock::now();
+    eng.scale(&pp);
+    hooks.scaling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    HPRLP_results r = eng.solve(&pp, &hooks);
+    fill_b200_info(eng, hooks, info);
+    return r;
+}
+
+}  // namespace
 
 // Row-partitioned solve of the synthetic uniform LP (m rows, n columns, K nonzeros per row) generated shard by shard
 // on the GPUs: the path for BASELINE.json config 5 (nnz = 6e9).  Each shard must have < 2^31 nonzeros.
 // obj_star receives the constructed optimal value <c, x*>.  With want_solution == 0 the x/y/z vectors are not
-// returned (result.x/y/z = NULL).
+// returned (result.x/y/z = NULL).  One host thread per GPU.
 extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, int K, unsigned long long seed,
                                                              const HPRLP_parameters *param_in, int n_gpus, int quiet,
                                                              int want_solution, double *obj_star, hprlp_b200_info *info) {
-    HPRLP_parameters def;
-    const HPRLP_parameters param = param_in ? *param_in : def;
-    int avail = 0;
-    if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) throw std::runtime_error("no CUDA device");
-    const int P = std::max(1, std::min(n_gpus, avail - param.device_number));
-    if (m <= 0 || n <= 0 || K <= 0 || K > n || K > 4096 || m > 2147483647LL) throw std::runtime_error("synth: bad dimensions");
-    if ((m + P - 1) / P * (long long)K >= 2147483647LL) throw std::runtime_error("synth: a shard would exceed 2^31 nonzeros; use more GPUs");
-    std::vector<long long> b(P + 1);
-    for (int p = 0; p <= P; ++p) b[p] = m * p / P;
-    std::vector<int> devs(P);
-    for (int p = 0; p < P; ++p) devs[p] = param.device_number + p;
-    std::vector<NcclComm> comms(P, nullptr);
-    if (P > 1) {
-        const int rc = nccl().CommInitAll(comms.data(), P, devs.data());
-        if (rc != 0) throw std::runtime_error(std::string("ncclCommInitAll failed: ") + nccl().GetErrorString(rc));
-    }
-    if (!quiet) std::printf("Synthetic uniform LP m=%lld n=%d nnz=%lld generated on %d GPU(s), row-block partitioned\n", m, n, m * K, P);
-
-    std::vector<HPRLP_results> results(P);
-    std::vector<SolveHooks> hooks(P);
-    std::vector<std::string> errors(P);
-    int bands0 = 0;   // column bands of GPU 0's row block (same policy on every GPU)
-    std::vector<double> objs(P, 0.0), gen_seconds(P, 0.0);
-    std::vector<std::thread> workers;
-    for (int p = 0; p < P; ++p) {
-        workers.emplace_back([&, p]() {
+    return abi_guard_results("hprlp_b200_solve_partitioned_synth", [&]() -> HPRLP_results {
+        HPRLP_parameters def;
+        const HPRLP_parameters param = param_in ? *param_in : def;
+        int avail = 0;
+        if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) throw std::runtime_error("no CUDA device");
+        const int P = std::max(1, std::min(n_gpus, avail - param.device_number));
+        const SynthSpec sp{m, n, K, seed};
+        check_synth(sp, P);
+        if (!quiet) std::printf("Synthetic uniform LP m=%lld n=%d nnz=%lld generated on %d GPU(s), row-block partitioned\n", m, n, m * K, P);
+        HPRLP_results out = abi_error_result();
+        hprlp_b200_info info0{};
+        double obj0 = 0.0;
+        if (P == 1) {
+            out = synth_rank(sp, 0, 1, param.device_number, nullptr, param, quiet != 0, &obj0, &info0);
+        } else {
+            std::vector<int> devs(P);
+            for (int p = 0; p < P; ++p) devs[p] = param.device_number + p;
+            std::vector<HPRLP_results> results(P, abi_error_result());
+            RankGroup group(Transport::Nccl, devs);
             try {
-                const int mp = (int)(b[p + 1] - b[p]);
-                const long long nnzp = (long long)mp * K;
-                HPRLP_parameters pp = param;
-                pp.device_number = devs[p];
-                Engine eng;
-                if (P > 1) { eng.comm = comms[p]; eng.nranks = P; eng.rank = p; eng.m_global = (int)m; eng.row0 = (int)b[p]; }
-                hooks[p].quiet = quiet != 0 || p != 0;
-                const auto t0 = std::chrono::steady_clock::now();
-                eng.prepare(mp, n, nnzp, devs[p]);
-                generate_rows(mp, b[p], K, n, seed, eng.A.rowPtr, eng.A.col, eng.A.val, eng.stream);
-                eng.finish_setup(true);
-                // vectors: x*, z* live in x_bar / z_bar until init_iterates() clears them
-                double *xs = eng.x_bar, *zs = eng.z_bar, *ys = eng.wm2, *ax = eng.wm, *w = eng.wn;
-                gen_col_vectors_kernel<<<1184, 256, 0, eng.stream>>>(n, seed, seed, eng.l, eng.u, xs, zs);
-                eng.spmv_A(xs, ax);
-                gen_row_vectors_kernel<<<1184, 256, 0, eng.stream>>>(mp, b[p], seed, seed, ax, eng.AL, eng.AU, ys);
-                eng.spmv_AT(ys, w);
-                eng.allreduce(w, (size_t)n);
-                HPR_CUDA_CHECK(cudaMemsetAsync(eng.d_scal, 0, sizeof(double), eng.stream));
-                gen_cost_kernel<<<1184, 256, 0, eng.stream>>>(n, w, zs, xs, eng.c, eng.d_scal);
-                HPR_CUDA_CHECK(cudaMemcpyAsync(&objs[p], eng.d_scal, sizeof(double), cudaMemcpyDeviceToHost, eng.stream));
-                HPR_CUDA_CHECK(cudaStreamSynchronize(eng.stream));
-                gen_seconds[p] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                hooks[p].setup_seconds = gen_seconds[p];
-                const auto t1 = std::chrono::steady_clock::now();
-                eng.scale(&pp);
-                hooks[p].scaling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-                if (p == 0) bands0 = (int)eng.A.bands.size();
-                results[p] = eng.solve(&pp, &hooks[p]);
-            } catch (const std::exception &e) {
-                errors[p] = e.what();
+                group.run([&](int p, int device, Collective *coll) {
+                    results[p] = synth_rank(sp, p, P, device, coll, param, quiet != 0 || p != 0, p == 0 ? &obj0 : nullptr, p == 0 ? &info0 : nullptr);
+                });
+            } catch (...) {
+                for (auto &r : results) { std::free(r.x); std::free(r.y); std::free(r.z); }
+                throw;
             }
-        });
-    }
-    for (auto &wk : workers) wk.join();
-    if (P > 1) for (int p = 0; p < P; ++p) nccl().CommDestroy(comms[p]);
-    for (int p = 0; p < P; ++p)
-        if (!errors[p].empty()) throw std::runtime_error("synthetic partitioned solve, GPU " + std::to_string(p) + ": " + errors[p]);
-    if (obj_star) *obj_star = objs[0];
-
-    HPRLP_results out = results[0];
-    if (want_solution) {
-        double *y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)m));
-        for (int p = 0; p < P; ++p)
-            if (results[p].y) std::memcpy(y + b[p], results[p].y, sizeof(double) * (size_t)(b[p + 1] - b[p]));
-        for (int p = 0; p < P; ++p) {
-            std::free(results[p].y);
-            if (p > 0) { std::free(results[p].x); std::free(results[p].z); }
+            for (int p = 1; p < P; ++p) { std::free(results[p].x); std::free(results[p].y); std::free(results[p].z); }
+            out = results[0];
         }
-        out.y = y;
-    } else {
-        for (int p = 0; p < P; ++p) { std::free(results[p].x); std::free(results[p].y); std::free(results[p].z); }
-        out.x = out.y = out.z = nullptr;
-    }
-    if (info) {
-        const SolveHooks &h = hooks[0];
-        std::memset(info, 0, sizeof(*info));
-        info->lambda_max = h.lambda_max; info->sigma = h.sigma; info->setup_seconds = h.setup_seconds;
-        info->scaling_seconds = h.scaling_seconds; info->power_seconds = h.power_seconds; info->loop_device_ms = h.loop_device_ms;
-        info->restarts = h.restarts; info->power_iters = h.power_iters; info->kernel_launches = h.kernel_launches;
-        info->b_scale = h.scal[0]; info->c_scale = h.scal[1]; info->norm_b = h.scal[2]; info->norm_c = h.scal[3];
-        info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
-        info->items_A = P; info->items_AT = P; info->bands_A = bands0;
-    }
-    return out;
+        if (!want_solution) { std::free(out.x); std::free(out.y); std::free(out.z); out.x = out.y = out.z = nullptr; }
+        if (obj_star) *obj_star = obj0;
+        if (info) *info = info0;
+        return out;
+    });
+}
+
+// The same, one process per GPU: this process generates and owns row block `rank` of `nranks` (NCCL communicator from
+// the unique id the caller distributed, see hprlp_b200_nccl_unique_id).
+extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth_rank(long long m, int n, int K, unsigned long long seed,
+                                                                  const HPRLP_parameters *param_in, const char *uid128, int rank,
+                                                                  int nranks, int quiet, int want_solution, double *obj_star,
+                                                                  hprlp_b200_info *info) {
+    return abi_guard_results("hprlp_b200_solve_partitioned_synth_rank", [&]() -> HPRLP_results {
+        HPRLP_parameters def;
+        const HPRLP_parameters param = param_in ? *param_in : def;
+        if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !uid128)) throw std::runtime_error("synth rank: bad arguments");
+        const SynthSpec sp{m, n, K, seed};
+        check_synth(sp, nranks);
+        std::unique_ptr<Collective> coll;
+        if (nranks > 1) coll.reset(open_nccl_rank(uid128, rank, nranks, param.device_number));
+        HPRLP_results out = synth_rank(sp, rank, nranks, param.device_number, coll.get(), param, quiet != 0, obj_star, info);
+        if (!want_solution) { std::free(out.x); std::free(out.y); std::free(out.z); out.x = out.y = out.z = nullptr; }
+        return out;
+    });
 }

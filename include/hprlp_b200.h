@@ -25,7 +25,7 @@ typedef struct {
     int lanes_A, lanes_AT;          /* per-matrix load-balance choice (lanes per row) */
     int items_A, items_AT;
     int bands_A;                    /* column bands of A (0 = single pass; >1 when n doubles exceed the L2 budget) */
-    int reserved0;
+    int reserved0;                  /* ranks of the row partition (1 = single GPU) */
 } hprlp_b200_info;
 
 /* HPRLP_main_solve with hooks.  power_z0 (host, length m) overrides the cuRAND start vector when
@@ -47,7 +47,9 @@ int hprlp_b200_power_start(int m, int device, double *out);
 hprlp_b200_engine *hprlp_b200_engine_create(const LP_info_cpu *model, const HPRLP_parameters *param);
 /* Runs `iters` more HPR iterations; returns the device time in ms (CUDA events on the engine stream). */
 double hprlp_b200_engine_run(hprlp_b200_engine *e, int iters);
-/* Average device time (ms) of one fused kernel launch: which = 0 x-phase (A^T pass), 1 y-phase (A pass). */
+/* Average device time (ms) of one launch: which = 0 fused x-phase (A^T pass), 1 fused y-phase (A pass); row-partitioned
+ * engines: 2 partial A_p^T y_p pass, 3 x-update on the owned x-block, 4 reduce-scatter + all-gather pair (collective:
+ * every rank calls it).  Timing only: the iterates are garbage afterwards. */
 double hprlp_b200_engine_time_phase(hprlp_b200_engine *e, int which, int reps);
 /* Current KKT residual / objective of the resident engine (one residual pass). */
 int hprlp_b200_engine_residuals(hprlp_b200_engine *e, double *kkt, double *primal_obj, double *dual_obj);
@@ -69,12 +71,34 @@ HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, i
                                                      const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
                                                      const HPRLP_parameters *param, int n_gpus);
 
-/* One LP row-block partitioned over n_gpus GPUs of one node (devices param->device_number ...): NCCL all-reduce of
- * A^T y per iteration over NVLink, fused y-phase on the local rows, all-reduce of <= 4 residual scalars per check.
- * Same results struct as solve(); no presolve.  n_gpus is clamped to the visible devices; 1 GPU = HPRLP_main_solve.
- * (new functionality; the reference is single-GPU) */
+/* One LP row-block partitioned over n_gpus GPUs of one node (devices param->device_number ...).  GPU p owns a block of
+ * rows of A (+ its transpose, y-side vectors) and the x-block J_p.  Per iteration: partial A_p^T y_p -> NCCL
+ * reduce-scatter over NVLink -> x-update on J_p -> NCCL all-gather of x_hat -> fused y-phase on the local rows;
+ * <= 9 residual scalars all-reduced per check.  Same results struct as solve() (x, z: n; y: m); no presolve.
+ * n_gpus is clamped to the visible devices; 1 GPU = HPRLP_main_solve.  One host thread per GPU (ncclCommInitAll).
+ * (new functionality; the reference is single-GPU, src/HPRLP.cu:51-64) */
 HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, const HPRLP_parameters *param, int n_gpus,
                                            int quiet, hprlp_b200_info *info);
+
+/* The same partitioned engine with n_ranks LOGICAL ranks that all live on device param->device_number; the exchanges
+ * are plain kernels between host barriers.  Parity-test path for single-GPU boxes (not for speed). */
+HPRLP_results hprlp_b200_solve_partitioned_local(const LP_info_cpu *model, const HPRLP_parameters *param, int n_ranks,
+                                                 int quiet, hprlp_b200_info *info);
+
+/* One process per GPU (torchrun / MPI style launch).  Rank 0 calls hprlp_b200_nccl_unique_id and distributes the 128
+ * bytes (bench.py: torch.distributed broadcast); every rank then passes the FULL host model, the id, its rank and the
+ * rank count; the rank uploads and owns its row block on device param->device_number.  All ranks return the full
+ * solution.  hprlp_b200_engine_create_rank is the resident-engine variant (hprlp_b200_engine_run etc. are collective:
+ * every rank calls them with the same arguments). */
+int hprlp_b200_nccl_unique_id(char *out128);
+HPRLP_results hprlp_b200_solve_partitioned_rank(const LP_info_cpu *model, const HPRLP_parameters *param, const char *uid128,
+                                                int rank, int nranks, int quiet, hprlp_b200_info *info);
+hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *model, const HPRLP_parameters *param,
+                                                 const char *uid128, int rank, int nranks);
+
+/* Diagnostic: ms of one in-place reduce-scatter + all-gather pair (out_ms[0]) and of one all-reduce (out_ms[1]) of
+ * `count` doubles over n_gpus GPUs, issued exactly as the partitioned solver issues them.  Returns 0 on success. */
+int hprlp_b200_nccl_exchange_ms(int n_gpus, long long count, int reps, double *out_ms);
 
 /* The synthetic "uniform" LP of BASELINE.json generated shard by shard ON the GPUs (same counter-based generator as
  * tools/synth_lp.c, bit-identical matrix) and solved row-partitioned: the path for instances whose CSR + transpose
@@ -83,6 +107,10 @@ HPRLP_results hprlp_b200_solve_partitioned(const LP_info_cpu *model, const HPRLP
 HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, int K, unsigned long long seed,
                                                  const HPRLP_parameters *param, int n_gpus, int quiet, int want_solution,
                                                  double *obj_star, hprlp_b200_info *info);
+/* The same with one process per GPU (see hprlp_b200_solve_partitioned_rank): this process generates row block `rank`. */
+HPRLP_results hprlp_b200_solve_partitioned_synth_rank(long long m, int n, int K, unsigned long long seed,
+                                                      const HPRLP_parameters *param, const char *uid128, int rank, int nranks,
+                                                      int quiet, int want_solution, double *obj_star, hprlp_b200_info *info);
 /* Test hook: rows [row0, row0+rows) of that matrix, generated on the device, copied to host (rows*K entries each). */
 int hprlp_b200_synth_rows(int n, int K, unsigned long long seed, long long row0, int rows, int *col_out, double *val_out);
 
@@ -91,6 +119,11 @@ int hprlp_b200_synth_rows(int n, int K, unsigned long long seed, long long row0,
  * hprlp_b200_presolve_free releases both. */
 int hprlp_b200_presolve(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);
 void hprlp_b200_presolve_free(void *handle, LP_info_cpu *reduced);
+
+/* Finished solves keep their device arena cached in a private stream-ordered memory pool (per device, bounded by
+ * HPRLP_POOL_RETAIN_MB, default 4096) so that repeated solve() calls skip cudaMalloc/cudaFree.  This call returns all
+ * cached memory to the driver (cudaMemPoolTrimTo 0).  The reference frees everything at the end of each solve. */
+void hprlp_b200_release_cached_memory(void);
 
 /* cudaProfilerStart/Stop of the library's (statically linked) CUDA runtime: lets `ncu --profile-from-start off`
  * capture only the timed region of bench.py. */

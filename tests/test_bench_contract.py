@@ -56,6 +56,9 @@ class _FakeLib:
     def solve(self, model, param, main=False):
         return dict(iter=520, time=0.25, status="OPTIMAL", primal_obj=-1.0, residuals=9e-5)
 
+    def release_cached_memory(self):
+        return None
+
 
 REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
             "dtype", "data", "config", "gpu_launches", "clocks", "roofline", "e2e", "cpu_baseline"}

@@ -1,6 +1,9 @@
-"""GPU (-m gpu, needs >= 2 GPUs): the row-block partitioned multi-GPU solve (NCCL all-reduce of A^T y over NVLink)
-against the single-GPU engine on the same LP: same status, same iteration count (same restart decisions), iterates
-to rounding (the cross-GPU sum changes the summation order of A^T y only)."""
+"""GPU (-m gpu): the row-block partitioned solve (x-block ownership: reduce-scatter of the partial A^T y, x-update on
+n/P entries, all-gather of x_hat) against the single-GPU engine on the same LP: same status, same iteration count (same
+restart decisions), iterates to rounding (the cross-rank sum changes the summation order of A^T y only).
+* `local` tests run on ONE GPU: P logical ranks of the same partitioned engine code with host-synchronised exchanges
+  (csrc/collective.cu) -- the partitioned path is parity-checked on every box;
+* NCCL tests need >= 2 GPUs (gpurun --gpus 2) and skip otherwise."""
 import numpy as np
 import pytest
 
@@ -28,6 +31,49 @@ def test_partitioned_matches_single_gpu(pkg, engine, kind, m, n, nnz):
         for k in "xyz":
             assert np.max(np.abs(one[k] - two[k])) <= 1e-8 * max(1.0, np.max(np.abs(one[k]))), (prm, k)
     assert abs(two["primal_obj"] - lp["obj_star"]) / (1 + abs(lp["obj_star"])) < 1e-5 or prm.get("max_iter")
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 4])
+@pytest.mark.parametrize("kind,m,n,nnz", [("uniform", 3000, 9000, 90000), ("powerlaw", 20000, 50000, 1000000)])
+def test_partitioned_local_ranks_match_single_gpu(pkg, engine, kind, m, n, nnz, ranks):
+    """P logical ranks on one GPU: row blocks, x-block ownership, every exchange -- against the plain engine."""
+    lp = pkg.synth_lp(kind, m, n, nnz, with_solution=True)
+    for prm in (dict(stop_tol=1e-6), dict(max_iter=300, stop_tol=1e-30)):
+        p = pkg.Parameters.default(use_presolve=False, **prm)
+        model = engine.create_model(lp)
+        one = engine.solve(model, p, main=True)
+        par = engine.solve_partitioned(model, p, n_gpus=ranks, local=True)
+        engine.free_model(model)
+        assert par["info"]["reserved0"] == ranks
+        assert one["status"] == par["status"] and one["iter"] == par["iter"], (prm, one["iter"], par["iter"])
+        assert abs(one["primal_obj"] - par["primal_obj"]) <= 1e-9 * (1 + abs(one["primal_obj"]))
+        for k in "xyz":
+            assert par[k].shape == one[k].shape
+            assert np.max(np.abs(one[k] - par[k])) <= 1e-8 * max(1.0, np.max(np.abs(one[k]))), (prm, k)
+
+
+def test_partitioned_local_ragged_blocks(pkg, engine):
+    """n not a multiple of the block size, more ranks than convenient, empty rows/columns: the padded exchange blocks."""
+    rng = np.random.default_rng(5)
+    m, n = 37, 131
+    dense = (rng.random((m, n)) < 0.08) * rng.normal(size=(m, n))
+    dense[5, :] = 0.0; dense[:, 7] = 0.0; dense[0, 0] = 1.0
+    rp = np.zeros(m + 1, np.int32); cols = []; vals = []
+    for i in range(m):
+        nzc = np.nonzero(dense[i])[0]
+        cols += list(nzc); vals += list(dense[i, nzc]); rp[i + 1] = len(cols)
+    xs = rng.random(n); ax = dense @ xs
+    lp = dict(m=m, n=n, rowPtr=rp, colIndex=np.array(cols, np.int32), values=np.array(vals), AL=ax - 0.5, AU=ax + 0.5,
+              l=np.zeros(n), u=np.full(n, 2.0), c=rng.normal(size=n))
+    p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-7, max_iter=20000)
+    model = engine.create_model(lp)
+    one = engine.solve(model, p, main=True)
+    for ranks in (2, 5):
+        par = engine.solve_partitioned(model, p, n_gpus=ranks, local=True)
+        assert one["status"] == par["status"] and one["iter"] == par["iter"], (ranks, one["iter"], par["iter"])
+        for k in "xyz":
+            assert np.max(np.abs(one[k] - par[k])) <= 1e-8 * max(1.0, np.max(np.abs(one[k]))), (ranks, k)
+    engine.free_model(model)
 
 
 def test_partitioned_single_gpu_falls_through(pkg, engine):

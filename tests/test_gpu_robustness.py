@@ -1,0 +1,81 @@
+"""GPU (-m gpu): behaviour at the edges of the C ABI -- nothing is thrown across it, cached device memory can be handed
+back, and the in-kernel look-back of rows cut by item boundaries is reproducible under concurrency."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_bytes():
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    return free
+
+
+def test_cuda_failure_becomes_error_status_not_an_exception(pkg, engine):
+    """A CUDA failure inside solve() (here: a device that does not exist) must come back as status "ERROR" with null
+    vectors, as the reference's own error results do (src/HPRLP.cu:66-79) -- never as a C++ exception through ctypes."""
+    lp = pkg.synth_lp("uniform", 300, 900, 3600)
+    model = engine.create_model(lp)
+    bad = pkg.Parameters.default(use_presolve=False, device_number=63)
+    r = engine.solve(model, bad, main=True)
+    assert r["status"] == "ERROR" and r["x"] is None and r["y"] is None and r["z"] is None
+    assert engine.lib.hprlp_b200_engine_create(model, C.byref(bad)) is None
+    rb = engine.solve_batched(model, np.zeros((2, 900)), np.zeros((2, 300)), np.zeros((2, 300)), np.zeros((2, 900)),
+                              np.ones((2, 900)), None, bad)
+    assert rb["status"] == ["ERROR", "ERROR"]
+    rp = engine.solve_partitioned(model, bad, n_gpus=2, local=True)
+    assert rp["status"] == "ERROR"
+    # the library is still usable afterwards
+    ok = engine.solve(model, pkg.Parameters.default(use_presolve=False, stop_tol=1e-6), main=True)
+    assert ok["status"] == "OPTIMAL"
+    engine.free_model(model)
+
+
+def test_release_cached_memory_returns_the_arena(pkg, engine):
+    """Finished solves keep their arena in the engines' private pool; hprlp_b200_release_cached_memory hands it back."""
+    import torch
+    torch.cuda.init()
+    lp = pkg.synth_lp("uniform", 100_000, 400_000, 8_000_000)     # arena of a few hundred MB
+    p = pkg.Parameters.default(use_presolve=False, max_iter=20, stop_tol=1e-30)
+    model = engine.create_model(lp)
+    engine.solve(model, p, main=True)                             # warm: context, modules, cuRAND
+    engine.release_cached_memory()
+    torch.cuda.synchronize()
+    before = _free_bytes()
+    engine.solve(model, p, main=True)
+    cached = before - _free_bytes()
+    engine.release_cached_memory()
+    after = _free_bytes()
+    engine.free_model(model)
+    assert cached > 150 << 20, f"the arena was expected to stay cached ({cached} bytes)"
+    assert before - after < 32 << 20, f"cached memory not returned: {before - after} bytes still held"
+
+
+def test_lookback_bitwise_reproducible_under_concurrency(pkg, engine):
+    """Rows longer than many 256-nonzero items force the in-kernel look-back (publish / consume of partial sums between
+    CTAs, chunk order from an atomic ticket).  Two engines solving concurrently on one GPU (two host threads, two
+    streams: CTAs of both kernels interleave on the SMs) must give bit-identical results to a solo run."""
+    lp = pkg.synth_lp("powerlaw", 3000, 40000, 3_000_000)         # mean row length 1000, longest rows ~ 40000 nonzeros
+    p = pkg.Parameters.default(use_presolve=False, max_iter=400, stop_tol=1e-30)
+    model = engine.create_model(lp)
+    solo = engine.solve(model, p, main=True)
+    outs = [None, None]
+
+    def work(i):
+        outs[i] = engine.solve(model, p, main=True)
+
+    for _ in range(2):
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for o in outs:
+            assert o["status"] == solo["status"] and o["iter"] == solo["iter"]
+            for k in "xyz":
+                assert np.array_equal(o[k], solo[k]), k
+    engine.free_model(model)

@@ -31,6 +31,9 @@ def _worker(rank, world, port, B, n, out_dir):
     local = np.sort(C[lo:hi], axis=1)                 # stand-in for solve_batched on the shard
     full = pkg.gather_shards(dist, local, B, world, rank)
     ms, units = pkg.reduce_time_units(dist, 10.0 + rank, hi - lo)
+    # the NCCL unique id of a partitioned-engine communicator travels from rank 0 to every rank the same way
+    uid = pkg.broadcast_unique_id(dist, lambda: bytes(range(128)), rank)
+    assert uid == bytes(range(128))
     if rank == 0:
         np.save(Path(out_dir) / "full.npy", full)
         np.save(Path(out_dir) / "tu.npy", np.array([ms, units]))
@@ -47,6 +50,20 @@ def test_batch_shard_gather_world2(tmp_path):
     assert np.array_equal(full, np.sort(rng.normal(size=(B, n)), axis=1))
     ms, units = np.load(tmp_path / "tu.npy")
     assert ms == 11.0 and units == B
+
+
+def test_row_blocks_cover_all_rows_and_balance_nonzeros():
+    """The row blocks of the partitioned solve (one per rank): contiguous, complete, balanced by nonzeros."""
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    lp = pkg.synth_lp("powerlaw", 5000, 9000, 120000)
+    rp = lp["rowPtr"]
+    for P in (1, 2, 3, 8):
+        b = pkg.row_blocks_by_nnz(rp, P)
+        assert b[0] == 0 and b[-1] == 5000 and all(b[i] <= b[i + 1] for i in range(P))
+        nz = [int(rp[b[i + 1]] - rp[b[i]]) for i in range(P)]
+        assert sum(nz) == int(rp[-1])
+        assert max(nz) - min(nz) <= 2 * int(np.max(np.diff(rp)))     # within two longest rows of the ideal split
 
 
 def test_shard_range_partitions_exactly():

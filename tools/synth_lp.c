@@ -109,6 +109,36 @@ void synth_lp_matrix_rows(int n, uint64_t seed, const int *rowPtr, int r0, int r
     }
 }
 
+/* "banded" twin (structured matrix of the same size): the columns of row i are drawn from a `window`-wide slice around
+ * i*n/m, so consecutive rows gather neighbouring entries (and so do the rows of the transpose). */
+void synth_lp_matrix_rows_banded(int m, int n, int window, uint64_t seed, const int *rowPtr, int r0, int r1, int *col, double *val) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = r0; i < r1; ++i) {
+        const int p0 = rowPtr[i], len = rowPtr[i + 1] - rowPtr[i];
+        int *c = col + p0;
+        int w = window < len ? len : window;
+        if (w > n) w = n;
+        long long lo = (long long)i * n / m - w / 2;
+        if (lo < 0) lo = 0;
+        if (lo + w > n) lo = n - w;
+        uint64_t ctr = 0;
+        for (int k = 0; k < len; ++k) c[k] = (int)(lo + (long long)(rng(seed, 2 + 4 * (uint64_t)i, ctr++) % (uint64_t)w));
+        for (;;) {
+            qsort(c, (size_t)len, sizeof(int), cmp_int);
+            int dup = 0;
+            for (int k = 1; k < len; ++k)
+                if (c[k] == c[k - 1]) { c[k - 1] = (int)(lo + (long long)(rng(seed, 2 + 4 * (uint64_t)i, ctr++) % (uint64_t)w)); dup = 1; }
+            if (!dup) break;
+        }
+        uint64_t vctr = 0;
+        for (int k = 0; k < len; ++k) {
+            double v;
+            do { v = 2.0 * u01(rng(seed, 3 + 4 * (uint64_t)i, vctr++)) - 1.0; } while (fabs(v) < 1e-3);
+            val[p0 + k] = v;
+        }
+    }
+}
+
 /* Draws (x*, y*, z*) with vec_seed and fills AL, AU, l, u, c; returns c'x*. */
 double synth_lp_vectors(int m, int n, const int *rowPtr, const int *col, const double *val, uint64_t seed,
                         uint64_t vec_seed, double *AL, double *AU, double *l, double *u, double *c,
