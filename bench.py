@@ -296,14 +296,13 @@ def run_engine_arm(args, pkg, spec, lp, local):
                 gpu_launches=t["launches"], wall_ms_per_step=t["wall_ms"] / args.steps, clocks=t["clocks"], roofline=roof)
 
 
-def run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist):
+def run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist, comm):
     """N > 1: ONE LP row-partitioned over the N GPUs, one process per GPU (this process = row block `rank`)."""
     eng = pkg.load_engine()
     m, n, nnz = lp["m"], lp["n"], int(lp["values"].shape[0])
     param = pkg.Parameters.default(stop_tol=0.0, use_presolve=False, device_number=local)
     model = eng.create_model(lp)
-    uid = fresh_uid(eng, dist, rank, local)
-    h = eng.lib.hprlp_b200_engine_create_rank(model, ctypes.byref(param), uid, rank, world)
+    h = eng.lib.hprlp_b200_engine_create_rank(model, ctypes.byref(param), comm)
     if not h:
         raise RuntimeError("engine_create_rank failed")
     warm = max(args.warmup, 3)
@@ -349,9 +348,11 @@ def run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist):
                            l2="per-GPU per-iteration working set %.0f MB > 126 MB L2 (no flush)" % (per_gpu / 1e6),
                            parallelism="row-block partitioned over %d GPUs (one process per GPU): reduce-scatter of partial A^T y + all-gather of x_hat "
                                        "blocks per iteration, NCCL over NVLink; x-block ownership" % world,
+                           exchange="fused reduce-scatter + x-update + all-gather kernel over NVLink peer memory (P2P loads/stores)"
+                                    if info.peer_exchange else "ncclReduceScatter + x-update kernel + ncclAllGather",
                            lanes_A=info.lanes_A, lanes_AT=info.lanes_AT),
                gpu_launches=t["launches"], wall_ms_per_step=t["wall_ms"] / args.steps, clocks=t["clocks"], roofline=roof,
-               partitioned=dict(ms_per_iteration=ms_iter, iters_per_s=1e3 / ms_iter, one_gpu_iters_per_s=one_gpu,
+               partitioned=dict(peer_exchange=bool(info.peer_exchange), ms_per_iteration=ms_iter, iters_per_s=1e3 / ms_iter, one_gpu_iters_per_s=one_gpu,
                                 speedup_vs_1gpu=(1e3 / ms_iter) / one_gpu if one_gpu else None, **parts))
     return out
 
@@ -377,14 +378,14 @@ def run_e2e(pkg, lib, lp, local, tol=1e-4):
                 residuals=r["residuals"], tol=tol)
 
 
-def run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist, tol=1e-4):
-    """The partitioned solve through the C ABI with HOST arrays on every rank (each uploads its row block)."""
+def run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist, comm, tol=1e-4):
+    """The partitioned solve through the C ABI with HOST arrays on every rank (each uploads its row block).  The
+    communicator handle exists already (like torch.distributed's process group, it is created once per job)."""
     param = pkg.Parameters.default(stop_tol=tol, use_presolve=False, device_number=local)
     model = eng.create_model(lp)
-    uid = fresh_uid(eng, dist, rank, local)
     barrier(dist, local)
     t0 = time.perf_counter()
-    r = eng.solve_partitioned_rank(model, param, uid, rank, world)
+    r = eng.solve_partitioned_rank(model, param, comm)
     wall = time.perf_counter() - t0
     eng.free_model(model)
     wall_max, _ = reduce_max_sum(dist, local, wall, 0)
@@ -470,7 +471,7 @@ def batched_summary(b):
 # ----------------------------------------------------------------------------------------------------------------
 # in-run parity of the multi-GPU paths (N > 1)
 # ----------------------------------------------------------------------------------------------------------------
-def run_parity(pkg, eng, rank, world, local, dist):
+def run_parity(pkg, eng, rank, world, local, dist, comm):
     out = {}
     lp = pkg.synth_lp(PARITY_LP["kind"], PARITY_LP["m"], PARITY_LP["n"], PARITY_LP["nnz"])
     ok_all = True
@@ -479,8 +480,7 @@ def run_parity(pkg, eng, rank, world, local, dist):
         p = pkg.Parameters.default(use_presolve=False, device_number=local, **prm)
         model = eng.create_model(lp)
         one = eng.solve(model, p, main=True)
-        uid = fresh_uid(eng, dist, rank, local)
-        par = eng.solve_partitioned_rank(model, p, uid, rank, world)
+        par = eng.solve_partitioned_rank(model, p, comm)
         eng.free_model(model)
         err = max(float(np.max(np.abs(one[k] - par[k])) / max(1.0, float(np.max(np.abs(one[k]))))) for k in "xyz")
         ok = one["status"] == par["status"] and one["iter"] == par["iter"] and err <= 1e-8
@@ -510,13 +510,12 @@ def run_parity(pkg, eng, rank, world, local, dist):
     return out
 
 
-def run_c5(pkg, eng, rank, world, local, dist):
+def run_c5(pkg, eng, rank, world, local, dist, comm):
     """configs[4]: nnz = 6e9, generated shard by shard on the GPUs, row-partitioned, solved to KKT < 1e-4."""
     p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-4, time_limit=300.0, device_number=local)
-    uid = fresh_uid(eng, dist, rank, local)
     barrier(dist, local)
     t0 = time.perf_counter()
-    r = eng.solve_partitioned_synth_rank(C5["m"], C5["n"], C5["K"], p, uid, rank, world, want_solution=False)
+    r = eng.solve_partitioned_synth_rank(C5["m"], C5["n"], C5["K"], p, comm, want_solution=False)
     wall = time.perf_counter() - t0
     wall, _ = reduce_max_sum(dist, local, wall, 0)
     if rank != 0:
@@ -638,6 +637,9 @@ def main():
     ap.add_argument("--no-single-ref", action="store_true", help="N > 1: skip the 1-GPU run that speedup_vs_1gpu is measured against")
     args = ap.parse_args()
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun exports OMP_NUM_THREADS=1; the host side (LP generator, oracle, model copies) is OpenMP/threads code
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // int(os.environ["WORLD_SIZE"])))
     pkg = graft.load_package()
     rank, world, local, dist = dist_setup(args.gpus)
     spec = WORKLOADS[args.workload]
@@ -685,11 +687,12 @@ def main():
             if not args.no_cpu:
                 out["cpu_baseline"] = cpu_baseline(pkg, lp, iters=10 if spec["nnz"] >= 5_000_000 else 200)
         else:
-            parity = run_parity(pkg, eng, rank, world, local, dist)
-            out = run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist)
+            comm = eng.comm_create(fresh_uid(eng, dist, rank, local), rank, world, local)   # one communicator for the whole run
+            parity = run_parity(pkg, eng, rank, world, local, dist, comm)
+            out = run_partitioned_arm(args, pkg, spec, lp, rank, world, local, dist, comm)
             e2e = None
             if not args.no_e2e:
-                runs = [run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist) for _ in range(2)]
+                runs = [run_e2e_partitioned(pkg, eng, lp, rank, world, local, dist, comm) for _ in range(2)]
                 e2e = dict(max(runs, key=lambda r: r["value"]), all_runs_time_to_tol_s=[r["time_to_tol_s"] for r in runs])
             eng.release_cached_memory()
             batched = None
@@ -698,7 +701,7 @@ def main():
             c5 = None
             if world == 8 and not args.no_c5 and args.workload == "c3":
                 eng.release_cached_memory()
-                c5 = run_c5(pkg, eng, rank, world, local, dist)
+                c5 = run_c5(pkg, eng, rank, world, local, dist, comm)
             if rank == 0:
                 out["parity"] = parity
                 if e2e is not None:
@@ -707,6 +710,7 @@ def main():
                     out["batched"] = batched
                 if c5 is not None:
                     out["c5"] = c5
+            eng.comm_destroy(comm)
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:

@@ -84,7 +84,7 @@ class B200Info(C.Structure):
                 ("b_scale", C.c_double), ("c_scale", C.c_double), ("norm_b", C.c_double), ("norm_c", C.c_double),
                 ("norm_b_org", C.c_double), ("norm_c_org", C.c_double),
                 ("lanes_A", C.c_int), ("lanes_AT", C.c_int), ("items_A", C.c_int), ("items_AT", C.c_int),
-                ("bands_A", C.c_int), ("reserved0", C.c_int)]
+                ("bands_A", C.c_int), ("reserved0", C.c_int), ("peer_exchange", C.c_int), ("reserved1", C.c_int)]
 
 
 REFERENCE_SYMBOLS = ["create_model_from_arrays", "create_model_from_mps", "solve", "free_model",
@@ -95,6 +95,7 @@ EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200
                     "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_solve_partitioned_synth", "hprlp_b200_synth_rows", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version",
                     "hprlp_b200_solve_partitioned_local", "hprlp_b200_nccl_unique_id", "hprlp_b200_solve_partitioned_rank",
                     "hprlp_b200_engine_create_rank", "hprlp_b200_nccl_exchange_ms", "hprlp_b200_solve_partitioned_synth_rank",
+                    "hprlp_b200_comm_create", "hprlp_b200_comm_destroy",
                     "hprlp_b200_release_cached_memory"]
 
 
@@ -176,17 +177,20 @@ class HprLib:
             L.hprlp_b200_solve_partitioned_local.argtypes = L.hprlp_b200_solve_partitioned.argtypes
             L.hprlp_b200_nccl_unique_id.restype = C.c_int
             L.hprlp_b200_nccl_unique_id.argtypes = [C.c_char_p]
+            L.hprlp_b200_comm_create.restype = C.c_void_p
+            L.hprlp_b200_comm_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+            L.hprlp_b200_comm_destroy.restype = None
+            L.hprlp_b200_comm_destroy.argtypes = [C.c_void_p]
             L.hprlp_b200_solve_partitioned_rank.restype = Results
-            L.hprlp_b200_solve_partitioned_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_char_p, C.c_int, C.c_int,
+            L.hprlp_b200_solve_partitioned_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_void_p,
                                                             C.c_int, C.POINTER(B200Info)]
             L.hprlp_b200_engine_create_rank.restype = C.c_void_p
-            L.hprlp_b200_engine_create_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_char_p, C.c_int, C.c_int]
+            L.hprlp_b200_engine_create_rank.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_void_p]
             L.hprlp_b200_nccl_exchange_ms.restype = C.c_int
             L.hprlp_b200_nccl_exchange_ms.argtypes = [C.c_int, C.c_longlong, C.c_int, c_double_p]
             L.hprlp_b200_solve_partitioned_synth_rank.restype = Results
             L.hprlp_b200_solve_partitioned_synth_rank.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(Parameters),
-                                                                  C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p,
-                                                                  C.POINTER(B200Info)]
+                                                                  C.c_void_p, C.c_int, C.c_int, c_double_p, C.POINTER(B200Info)]
             L.hprlp_b200_release_cached_memory.restype = None
             L.hprlp_b200_release_cached_memory.argtypes = []
 
@@ -273,22 +277,31 @@ class HprLib:
             raise RuntimeError("hprlp_b200_nccl_unique_id failed")
         return buf.raw
 
-    def solve_partitioned_rank(self, model, param, uid, rank, nranks, quiet=True):
-        """One process per GPU: this process owns row block `rank`; every rank gets the full solution."""
+    def comm_create(self, uid, rank, nranks, device):
+        """This rank's endpoint of a process-per-GPU partitioned solve (NCCL communicator); reuse it across solves."""
+        h = self.lib.hprlp_b200_comm_create(uid, int(rank), int(nranks), int(device))
+        if not h:
+            raise RuntimeError("hprlp_b200_comm_create failed")
+        return h
+
+    def comm_destroy(self, comm):
+        self.lib.hprlp_b200_comm_destroy(comm)
+
+    def solve_partitioned_rank(self, model, param, comm, quiet=True):
+        """One process per GPU: this process owns one row block; every rank gets the full solution."""
         mm = model.contents
         info = B200Info()
-        res = self.lib.hprlp_b200_solve_partitioned_rank(model, C.byref(param), uid, int(rank), int(nranks), 1 if quiet else 0,
-                                                         C.byref(info))
+        res = self.lib.hprlp_b200_solve_partitioned_rank(model, C.byref(param), comm, 1 if quiet else 0, C.byref(info))
         out = self._take(res, mm.m, mm.n)
         out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         return out
 
-    def solve_partitioned_synth_rank(self, m, n, K, param, uid, rank, nranks, seed=None, want_solution=False, quiet=True):
+    def solve_partitioned_synth_rank(self, m, n, K, param, comm, seed=None, want_solution=False, quiet=True):
         info = B200Info()
         obj = C.c_double(0.0)
         res = self.lib.hprlp_b200_solve_partitioned_synth_rank(int(m), int(n), int(K), SEED if seed is None else seed, C.byref(param),
-                                                               uid, int(rank), int(nranks), 1 if quiet else 0,
-                                                               1 if want_solution else 0, C.byref(obj), C.byref(info))
+                                                               comm, 1 if quiet else 0, 1 if want_solution else 0, C.byref(obj),
+                                                               C.byref(info))
         out = self._take(res, int(m), int(n))
         out["info"] = {f[0]: getattr(info, f[0]) for f in B200Info._fields_}
         out["obj_star"] = obj.value

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <exception>
 
+#include <cuda_runtime.h>
+
 #include "../../include/structs.h"
 
 namespace hpr {
@@ -33,6 +35,7 @@ inline R abi_guard(const char *where, F &&body, E &&on_error) {
     } catch (...) {
         abi_report(where, "unknown exception");
     }
+    cudaGetLastError();   // a recoverable CUDA error must not be found again by the next call's cudaGetLastError check
     return on_error();
 }
 

@@ -69,7 +69,6 @@ void fill_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info) { 
 }  // namespace
 
 struct hprlp_b200_engine {
-    std::unique_ptr<hpr::Collective> coll;   // rank of a row-partitioned engine (declared first: destroyed after eng)
     Engine eng;
     HPRLP_parameters param;
     SolveHooks hooks;
@@ -162,21 +161,21 @@ hprlp_b200_engine *hprlp_b200_engine_create(const LP_info_cpu *lp, const HPRLP_p
 
 // Resident engine of ONE RANK of a row-partitioned solve (one process per GPU): this process uploads row block `rank`
 // of the model to device param->device_number; all ranks then call hprlp_b200_engine_run with the same arguments.
-hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *lp, const HPRLP_parameters *param_in, const char *uid128,
-                                                 int rank, int nranks) {
-    if (!lp || !lp->A || nranks < 1 || rank < 0 || rank >= nranks) return nullptr;
-    if (nranks == 1) return hprlp_b200_engine_create(lp, param_in);
-    if (!uid128 || nranks > lp->m) return nullptr;
+hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *lp, const HPRLP_parameters *param_in, hprlp_b200_comm *comm) {
+    if (!lp || !lp->A) return nullptr;
+    if (!comm || !comm->coll) return hprlp_b200_engine_create(lp, param_in);
+    if (comm->coll->nranks > lp->m) return nullptr;
     return hpr::abi_guard<hprlp_b200_engine *>("hprlp_b200_engine_create_rank", [&]() -> hprlp_b200_engine * {
         HPRLP_parameters def;
         std::unique_ptr<hprlp_b200_engine> h(new hprlp_b200_engine);
         h->param = param_in ? *param_in : def;
+        h->param.device_number = comm->device;
         h->hooks.quiet = true;
-        h->coll.reset(hpr::open_nccl_rank(uid128, rank, nranks, h->param.device_number));
-        const std::vector<int> b = hpr::row_blocks_by_nnz(lp->A->rowPtr, lp->m, nranks);
-        h->eng.set_partition(h->coll.get(), lp->m, b[rank]);
+        hpr::Collective *coll = comm->coll.get();
+        const std::vector<int> b = hpr::row_blocks_by_nnz(lp->A->rowPtr, lp->m, coll->nranks);
+        h->eng.set_partition(coll, lp->m, b[coll->rank]);
         const double t0 = now_seconds();
-        hpr::upload_row_block(h->eng, lp, b[rank], b[rank + 1], h->param.device_number);
+        hpr::upload_row_block(h->eng, lp, b[coll->rank], b[coll->rank + 1], comm->device);
         h->hooks.setup_seconds = now_seconds() - t0;
         const double t1 = now_seconds();
         h->eng.scale(&h->param);

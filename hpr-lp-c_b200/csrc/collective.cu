@@ -1,7 +1,13 @@
 // collective.cu -- transports of the row-partitioned exchange steps (see collective.h).
 #include "collective.h"
 
+#include <unistd.h>
+
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
 #include <condition_variable>
 #include <mutex>
 #include <stdexcept>
@@ -155,6 +161,132 @@ class LocalCollective : public Collective {
 }  // namespace
 
 Collective *make_nccl_collective(NcclComm comm, int nranks, int rank) { return new NcclCollective(comm, nranks, rank); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// peer-memory exchange bootstrap
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerRecord {   // what a rank tells the others about its exchange buffers (padded to 32 doubles)
+    long long pid;
+    int device, ok;
+    void *w, *xhat, *flags;
+    cudaIpcMemHandle_t hw, hx, hf;
+};
+static_assert(sizeof(PeerRecord) <= 32 * sizeof(double), "PeerRecord must fit its all-gather slot");
+constexpr size_t kRecDoubles = 32;
+
+// every rank contributes ok (1/0); returns true iff all ranks said 1
+bool all_ranks_ok(Collective *coll, bool ok, double *dbuf, cudaStream_t st) {
+    double v = ok ? 0.0 : 1.0;
+    check_cuda(cudaMemcpyAsync(dbuf, &v, sizeof(double), cudaMemcpyHostToDevice, st), "peer exchange vote");
+    coll->all_reduce(dbuf, 1, false, st);
+    check_cuda(cudaMemcpyAsync(&v, dbuf, sizeof(double), cudaMemcpyDeviceToHost, st), "peer exchange vote");
+    check_cuda(cudaStreamSynchronize(st), "peer exchange vote");
+    return v == 0.0;
+}
+}  // namespace
+
+PeerExchange *peer_exchange_create(Collective *coll, int device, size_t npad, cudaStream_t st) {
+    const int P = coll->nranks, rank = coll->rank;
+    if (P < 2 || P > kMaxPeers || std::string(coll->name()) != "nccl") return nullptr;
+    if (const char *e = getenv("HPRLP_EXCHANGE"))
+        if (std::string(e) == "nccl") return nullptr;   // same value on every rank (environment of one job)
+    std::unique_ptr<PeerExchange> px(new PeerExchange);
+    px->P = P; px->rank = rank; px->device = device; px->npad = npad;
+    double *dbuf = nullptr;   // bootstrap all-gather buffer
+    check_cuda(cudaMalloc(&dbuf, sizeof(double) * kRecDoubles * P), "peer exchange bootstrap");
+    PeerRecord mine{};
+    mine.pid = (long long)getpid();
+    mine.device = device;
+    bool ok = true;
+    ok = ok && cudaMalloc(&px->w[rank], sizeof(double) * npad) == cudaSuccess;
+    ok = ok && cudaMalloc(&px->xhat[rank], sizeof(double) * npad) == cudaSuccess;
+    ok = ok && cudaMalloc(&px->flags[rank], sizeof(unsigned long long) * 2 * kMaxPeers) == cudaSuccess;
+    ok = ok && cudaMalloc(&px->done, sizeof(unsigned)) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(px->w[rank], 0, sizeof(double) * npad, st);
+        cudaMemsetAsync(px->xhat[rank], 0, sizeof(double) * npad, st);
+        cudaMemsetAsync(px->flags[rank], 0, sizeof(unsigned long long) * 2 * kMaxPeers, st);
+        cudaMemsetAsync(px->done, 0, sizeof(unsigned), st);
+        mine.w = px->w[rank]; mine.xhat = px->xhat[rank]; mine.flags = px->flags[rank];
+        ok = ok && cudaIpcGetMemHandle(&mine.hw, px->w[rank]) == cudaSuccess;
+        ok = ok && cudaIpcGetMemHandle(&mine.hx, px->xhat[rank]) == cudaSuccess;
+        ok = ok && cudaIpcGetMemHandle(&mine.hf, px->flags[rank]) == cudaSuccess;
+    }
+    cudaGetLastError();
+    mine.ok = ok ? 1 : 0;
+    std::vector<double> host(kRecDoubles * P, 0.0);
+    std::memcpy(host.data() + kRecDoubles * rank, &mine, sizeof(mine));
+    check_cuda(cudaMemcpyAsync(dbuf + kRecDoubles * rank, host.data() + kRecDoubles * rank, sizeof(double) * kRecDoubles, cudaMemcpyHostToDevice, st), "peer exchange bootstrap");
+    coll->all_gather_inplace(dbuf, kRecDoubles, st);
+    check_cuda(cudaMemcpyAsync(host.data(), dbuf, sizeof(double) * kRecDoubles * P, cudaMemcpyDeviceToHost, st), "peer exchange bootstrap");
+    check_cuda(cudaStreamSynchronize(st), "peer exchange bootstrap");
+    for (int q = 0; q < P && ok; ++q) {
+        PeerRecord r;
+        std::memcpy(&r, host.data() + kRecDoubles * q, sizeof(r));
+        if (!r.ok) { ok = false; break; }
+        if (q == rank) continue;
+        if (r.pid == mine.pid) {   // same process (one host thread per GPU): raw pointers + peer access
+            int can = 0;
+            if (r.device != device) {
+                cudaDeviceCanAccessPeer(&can, device, r.device);
+                if (!can) { ok = false; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(r.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = false; break; }
+                cudaGetLastError();
+            }
+            px->w[q] = static_cast<double *>(r.w); px->xhat[q] = static_cast<double *>(r.xhat);
+            px->flags[q] = static_cast<unsigned long long *>(r.flags);
+        } else {                   // another process: CUDA IPC (enables peer access lazily)
+            void *a = nullptr, *b = nullptr, *c = nullptr;
+            if (cudaIpcOpenMemHandle(&a, r.hw, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&b, r.hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&c, r.hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                if (a) cudaIpcCloseMemHandle(a);
+                if (b) cudaIpcCloseMemHandle(b);
+                cudaGetLastError();
+                ok = false;
+                break;
+            }
+            px->w[q] = static_cast<double *>(a); px->xhat[q] = static_cast<double *>(b);
+            px->flags[q] = static_cast<unsigned long long *>(c);
+            px->ipc_opened[q] = true;
+        }
+    }
+    const bool all_ok = all_ranks_ok(coll, ok, dbuf, st);
+    cudaFree(dbuf);
+    if (!all_ok) {
+        if (rank == 0) std::fprintf(stderr, "[hprlp] peer-memory exchange unavailable (no P2P / IPC mapping): using NCCL reduce-scatter + all-gather\n");
+        PeerExchange *raw = px.release();
+        // nobody uses the buffers: plain local teardown (the vote above was the barrier)
+        for (int q = 0; q < P; ++q)
+            if (raw->ipc_opened[q]) { cudaIpcCloseMemHandle(raw->w[q]); cudaIpcCloseMemHandle(raw->xhat[q]); cudaIpcCloseMemHandle(raw->flags[q]); }
+        cudaFree(raw->w[rank]); cudaFree(raw->xhat[rank]); cudaFree(raw->flags[rank]); cudaFree(raw->done);
+        delete raw;
+        cudaGetLastError();
+        return nullptr;
+    }
+    return px.release();
+}
+
+void peer_exchange_destroy(PeerExchange *px, Collective *coll, cudaStream_t st) {
+    if (!px) return;
+    // nobody may unmap or free while a peer can still touch the buffers: agree that everyone is done first
+    try {
+        double *dbuf = nullptr;
+        if (cudaMalloc(&dbuf, sizeof(double)) == cudaSuccess) {
+            all_ranks_ok(coll, true, dbuf, st);
+            cudaFree(dbuf);
+        }
+    } catch (...) {
+        // a peer failed: its communicator was aborted; fall through and release what is ours
+    }
+    for (int q = 0; q < px->P; ++q)
+        if (px->ipc_opened[q]) { cudaIpcCloseMemHandle(px->w[q]); cudaIpcCloseMemHandle(px->xhat[q]); cudaIpcCloseMemHandle(px->flags[q]); }
+    cudaFree(px->w[px->rank]); cudaFree(px->xhat[px->rank]); cudaFree(px->flags[px->rank]); cudaFree(px->done);
+    cudaGetLastError();
+    delete px;
+}
 
 LocalGroup *local_group_create(int nranks) {
     if (nranks < 1 || nranks > kMaxLocalRanks) throw std::runtime_error("local collective: 1..16 ranks");

@@ -37,6 +37,34 @@ class Collective {
 
 Collective *make_nccl_collective(NcclComm comm, int nranks, int rank);   // takes ownership of the communicator
 
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange (NVLink 5 / NVSwitch P2P): the per-iteration exchange of the row-partitioned mode as ONE kernel
+// of ours instead of two NCCL collectives.  Every rank exposes three cudaMalloc'ed buffers to all the others (raw
+// pointers + cudaDeviceEnablePeerAccess inside one process, CUDA IPC handles between processes; the bootstrap runs
+// over the rank's NCCL communicator):
+//   w      npad doubles: the partial A_p^T y_p this rank's SpMV pass writes
+//   xhat   npad doubles: the full x_hat this rank's fused y-phase gathers from
+//   flags  2 x 16 epochs: A[q] = "rank q's partial w of epoch e is complete", B[q] = "rank q has stored its x_hat
+//          block of epoch e everywhere" -- written remotely by rank q (st.release.sys), polled locally (ld.acquire.sys)
+// fused_exchange_x_kernel (engine.cu): wait A -> for j in the owned x-block: w_j = sum_q w_q[j] over P2P loads in
+// rank order (deterministic), x-update, x_hat_j stored into EVERY rank's xhat over P2P -> last CTA signals B.
+// NVLink traffic per GPU per iteration: 8 n (P-1)/P bytes in (loads) and the same out (stores), overlapped.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerExchange {
+    int P = 1, rank = 0, device = 0;
+    size_t npad = 0;
+    double *w[kMaxPeers] = {};
+    double *xhat[kMaxPeers] = {};
+    unsigned long long *flags[kMaxPeers] = {};   // flags[q] + 0..15: A slots, + 16..31: B slots (memory of rank q)
+    unsigned *done = nullptr;                    // local: CTAs of the fused kernel that finished
+    unsigned long long epoch = 0;                // exchanges issued so far (same on every rank)
+    bool ipc_opened[kMaxPeers] = {};
+};
+// Collective calls (every rank, same order).  create returns nullptr on every rank if any rank cannot map its peers.
+PeerExchange *peer_exchange_create(Collective *coll, int device, size_t npad, cudaStream_t st);
+void peer_exchange_destroy(PeerExchange *px, Collective *coll, cudaStream_t st);
+
 struct LocalGroup;   // shared state of P in-process logical ranks
 LocalGroup *local_group_create(int nranks);
 void local_group_destroy(LocalGroup *g);

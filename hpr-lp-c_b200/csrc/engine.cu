@@ -210,6 +210,82 @@ __global__ void __launch_bounds__(kVecThreads) x_update_kernel(const double *w, 
         if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
     }
 }
+// ---- the same exchange + x-update as ONE kernel over NVLink peer memory (collective.h, PeerExchange) ------------------
+struct PeerPtrs {
+    const double *w[kMaxPeers];
+    double *xhat[kMaxPeers];
+    unsigned long long *flags[kMaxPeers];
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer(const double *p) {   // never served from this SM's L1 (peer lines are L1-cacheable)
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polls a flag of THIS GPU's memory that a peer GPU writes.  Different GPUs run concurrently, so the wait is finite; the
+// bound turns a protocol bug or a dead peer into a trapped context (-> "ERROR" result) instead of a hung GPU.
+__device__ __forceinline__ void wait_epoch(const unsigned long long *flag, unsigned long long epoch) {
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(100);
+        if (++spins > (1u << 27)) __trap();
+    }
+}
+// "my partial w (slot 0) / my x_hat stores (slot 1) of this epoch are complete": one release store into every rank's flags
+__global__ void exchange_signal_kernel(PeerPtrs pp, int P, int rank, int slot, unsigned long long epoch) {
+    if ((int)threadIdx.x < P) {
+        __threadfence_system();
+        st_release_sys(pp.flags[threadIdx.x] + slot * kMaxPeers + rank, epoch);
+    }
+}
+__global__ void exchange_wait_kernel(const unsigned long long *flags, int P, int slot, unsigned long long epoch) {
+    if ((int)threadIdx.x < P) wait_epoch(flags + slot * kMaxPeers + threadIdx.x, epoch);
+}
+// reduce-scatter + x-update + all-gather of one HPR iteration for the x-block [j0, j1) this GPU owns:
+//   wait until every rank's partial w_q = A_q^T y_q is complete;  w_j = sum_q w_q[j] (P2P loads, rank order: the result
+//   does not depend on who finishes first);  x-update (same arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY
+//   rank's x_hat buffer (P2P stores);  the last CTA tells every rank that this block of x_hat is in place.
+template <bool CHECK>
+__global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs pp, int P, int rank, unsigned long long epoch, unsigned *done,
+                                                                      double *x, const double *c, const double *l, const double *u,
+                                                                      const double *x0, double *x_bar, double *z_bar, double *x_tmp,
+                                                                      const double *params, const int *kx, int *ky, int j0, int j1) {
+    if ((int)threadIdx.x < P) wait_epoch(pp.flags[rank] + threadIdx.x, epoch);
+    __syncthreads();
+    const double sigma = params[0];
+    const int k = *kx;
+    const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
+    for (int j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += gridDim.x * blockDim.x) {
+        double w = 0.0;
+        for (int q = 0; q < P; ++q) w += ld_peer(pp.w[q] + j);
+        const double xi = x[j];
+        const double zt = fma(sigma, w - c[j], xi);
+        const double xb = fmin(u[j], fmax(l[j], zt));
+        const double xh = 2.0 * xb - xi;
+        x[j] = fma(f2, xh, f1 * x0[j]);
+        for (int q = 0; q < P; ++q) pp.xhat[q][j] = xh;
+        if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
+    }
+    __threadfence_system();   // this thread's peer stores are performed before the CTA is counted as done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {
+            *done = 0u;
+            __threadfence_system();
+            for (int q = 0; q < P; ++q) st_release_sys(pp.flags[q] + kMaxPeers + rank, epoch);
+        }
+    }
+}
+
 // dual residual terms from the reduce-scattered w = (A^T y_bar)_{J_p} (same slots as ResidualDualOp; sums over J_p)
 template <bool GAP, bool ITER0>
 __global__ void __launch_bounds__(kVecThreads) residual_dual_kernel(const double *w, const double *c, const double *z_bar, const double *x_bar,
@@ -438,7 +514,7 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.item_row = dalloc<int>(witems + 1);
     M.head_part = dalloc<PartSlot>(witems * 2);   // all-ones = "not published" (set in finish_matrix); consumers re-arm what they read
     M.tail_part = dalloc<PartSlot>(witems * 2);
-    M.ticket = dalloc<unsigned>(2);
+    M.ticket = dalloc<unsigned long long>(1);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
@@ -467,7 +543,7 @@ void Engine::finish_matrix(DevCsr &M) {
     const size_t part_bytes = sizeof(PartSlot) * (size_t)M.n_items * kWarps * 2;
     HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0xFF, part_bytes, stream));   // every packet "not published"
     HPR_CUDA_CHECK(cudaMemsetAsync(M.tail_part, 0xFF, part_bytes, stream));
-    HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, 2 * sizeof(unsigned), stream));
+    HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned long long), stream));
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
 }
 
@@ -499,7 +575,7 @@ void Engine::build_bands(DevCsr &M) {
         o_item[b] = total; total += up((wit + 1) * sizeof(int));
         o_head[b] = total; total += up(wit * 2 * sizeof(PartSlot));
         o_tail[b] = total; total += up(wit * 2 * sizeof(PartSlot));
-        o_tick[b] = total; total += up(2 * sizeof(unsigned));
+        o_tick[b] = total; total += up(sizeof(unsigned long long));
     }
     const size_t o_carry = total; total += up((size_t)M.rows * sizeof(double));
     const size_t o_ptrs = total;  total += up(sizeof(void *) * 2 * nb);
@@ -517,7 +593,7 @@ void Engine::build_bands(DevCsr &M) {
         Bd.item_row = reinterpret_cast<int *>(store + o_item[b]);
         Bd.head_part = reinterpret_cast<PartSlot *>(store + o_head[b]);
         Bd.tail_part = reinterpret_cast<PartSlot *>(store + o_tail[b]);
-        Bd.ticket = reinterpret_cast<unsigned *>(store + o_tick[b]);
+        Bd.ticket = reinterpret_cast<unsigned long long *>(store + o_tick[b]);
         ptrs[b] = Bd.col; ptrs[nb + b] = Bd.val;
     }
     HPR_CUDA_CHECK(cudaMemcpyAsync(store + o_ptrs, ptrs.data(), sizeof(void *) * 2 * nb, cudaMemcpyHostToDevice, stream));
@@ -536,8 +612,12 @@ void Engine::build_bands(DevCsr &M) {
 
 void Engine::alloc_common() {
     const size_t nv = dist() ? npad : (size_t)n;   // partitioned: exchange buffers hold nranks equal blocks
-    x = dalloc<double>(nv); x0 = dalloc<double>(nv); x_hat = dalloc<double>(nv); x_bar = dalloc<double>(nv);
-    z_bar = dalloc<double>(nv); x_tmp = dalloc<double>(nv); wn = dalloc<double>(nv);
+    if (dist()) px = peer_exchange_create(coll, device, npad, stream);   // collective: every rank, same point of the setup
+    x = dalloc<double>(nv); x0 = dalloc<double>(nv); x_bar = dalloc<double>(nv);
+    z_bar = dalloc<double>(nv); x_tmp = dalloc<double>(nv);
+    // the two exchanged vectors live in peer-visible (cudaMalloc + IPC) memory when the NVLink exchange is on
+    x_hat = px ? px->xhat[rank] : dalloc<double>(nv);
+    wn = px ? px->w[rank] : dalloc<double>(nv);
     y = dalloc<double>(m); y0 = dalloc<double>(m); y_bar = dalloc<double>(m); y_obj = dalloc<double>(m);
     y_tmp = dalloc<double>(m); wm = dalloc<double>(m); wm2 = dalloc<double>(m);
     row_norm = dalloc<double>(m); col_norm = dalloc<double>(n);
@@ -724,6 +804,7 @@ Engine::~Engine() {
     t[1] = now_seconds();
     for (cudaTextureObject_t tx : {tex_y, tex_xhat, tex_q, tex_atq})
         if (tx) cudaDestroyTextureObject(tx);
+    if (px) { peer_exchange_destroy(px, coll, stream); px = nullptr; }   // collective: agrees that no peer still uses the buffers
     t[2] = now_seconds();
     for (DevCsr *M : {&A, &AT}) {
         if (M->band_store) cudaFree(M->band_store);
@@ -976,6 +1057,27 @@ void Engine::upload_params() {   // reference reset_/upload_halpern_*_params, sr
 
 void Engine::reset_halpern_counter() { HPR_CUDA_CHECK(cudaMemsetAsync(d_k, 0, 2 * sizeof(int), stream)); }
 
+// wn holds this rank's partial A_p^T y_p.  On return x (owned block) is updated and x_hat is complete on every rank.
+void Engine::exchange_x(bool check) {
+    const int gx = vec_grid(xb1 - xb0);
+    if (px) {
+        PeerPtrs pp;
+        for (int q = 0; q < kMaxPeers; ++q) { pp.w[q] = px->w[q]; pp.xhat[q] = px->xhat[q]; pp.flags[q] = px->flags[q]; }
+        const unsigned long long e = ++px->epoch;
+        exchange_signal_kernel<<<1, 32, 0, stream>>>(pp, nranks, rank, 0, e);
+        if (check) fused_exchange_x_kernel<true><<<gx, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, xb0, xb1);
+        else fused_exchange_x_kernel<false><<<gx, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+        exchange_wait_kernel<<<1, 32, 0, stream>>>(px->flags[rank], nranks, 1, e);
+        launches += 3;
+        return;
+    }
+    coll->reduce_scatter_inplace(wn, xblock, stream);
+    if (check) x_update_kernel<true><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, xb0, xb1);
+    else x_update_kernel<false><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+    coll->all_gather_inplace(x_hat, xblock, stream);
+    launches += 1;
+}
+
 void Engine::launch_iteration(bool check) {
     if (dist()) {
         // Row-partitioned iteration: partial w_p = A_p^T y_p over the local rows, reduce-scatter so that this
@@ -983,24 +1085,19 @@ void Engine::launch_iteration(bool check) {
         // y-phase on the local rows of A with the full x_hat.
         SpmvOp<false, true> ow; ow.g = y; ow.tex = tex_y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
         launch_stream_hot(AT, ow, stream);
-        coll->reduce_scatter_inplace(wn, xblock, stream);
-        const int gx = vec_grid(xb1 - xb0);
+        exchange_x(check);
         if (check) {
-            x_update_kernel<true><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, xb0, xb1);
-            coll->all_gather_inplace(x_hat, xblock, stream);
             YPhaseOp<true> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         } else {
-            x_update_kernel<false><<<gx, kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
-            coll->all_gather_inplace(x_hat, xblock, stream);
             YPhaseOp<false> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
             oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
             launch_stream_hot(A, oy, stream);
         }
-        launches += 3;
+        launches += 2;
         return;
     }
     if (check) {
@@ -1254,7 +1351,8 @@ double Engine::time_phase_ms(int which, int reps) {
         } else if (which == 3) {   // row-partitioned x-update on the owned block (from whatever wn holds)
             x_update_kernel<false><<<vec_grid(xb1 - xb0), kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
         } else if (which == 4) {   // the two exchanges of one iteration, as the loop issues them
-            if (coll) { coll->reduce_scatter_inplace(wn, xblock, stream); coll->all_gather_inplace(x_hat, xblock, stream); }
+            if (coll && px) exchange_x(false);   // peer-memory path: the exchange IS the fused x-update kernel
+            else if (coll) { coll->reduce_scatter_inplace(wn, xblock, stream); coll->all_gather_inplace(x_hat, xblock, stream); }
         } else {
             YPhaseOp<false> oy;
             oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;

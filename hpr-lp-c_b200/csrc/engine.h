@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <limits>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -42,7 +43,7 @@ struct DevCsr {
     int *item_row = nullptr;
     int n_items = 0;
     PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries (all-ones = empty)
-    unsigned *ticket = nullptr;   // [2] chunk ticket + finished-CTA counter of csr_stream_kernel (zero between launches)
+    unsigned long long *ticket = nullptr;   // chunk tickets handed out by csr_stream_kernel over all launches (kernels.cuh)
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
@@ -146,6 +147,8 @@ class Engine {
     // n-vectors are allocated with npad = nranks * xblock entries so both exchanges run in place.
     // coll == nullptr: single GPU.
     Collective *coll = nullptr;
+    PeerExchange *px = nullptr;    // NVLink peer-memory exchange (collective.h); null: NCCL reduce-scatter + all-gather
+    void exchange_x(bool check);   // reduce-scatter + x-update on the owned block + all-gather, by either transport
     int nranks = 1, rank = 0, m_global = 0, row0 = 0;
     int xb0 = 0, xb1 = 0;          // owned columns
     size_t xblock = 0, npad = 0;   // exchange block (multiple of 64 entries), padded n-vector length
@@ -209,6 +212,13 @@ void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, cons
 std::vector<int> row_blocks_by_nnz(const int *rowPtr, int m, int P);
 void upload_row_block(Engine &eng, const LP_info_cpu *model, int r0, int r1, int device);
 Collective *open_nccl_rank(const char *uid128, int rank, int nranks, int device);
+}  // namespace hpr
+// one rank's endpoint of a process-per-GPU partitioned solve (include/hprlp_b200.h)
+struct hprlp_b200_comm {
+    std::unique_ptr<hpr::Collective> coll;
+    int device = 0;
+};
+namespace hpr {
 void fill_b200_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info);
 
 // device memory pool of the engines (engine.cu)

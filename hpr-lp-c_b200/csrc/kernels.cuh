@@ -76,7 +76,8 @@ struct CsrView {
     int n_items;          // CTAs in the grid
     PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
     PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
-    unsigned *ticket;     // [2]: {next chunk to hand out, CTAs finished}; both zero between launches
+    unsigned long long *ticket;   // chunk tickets handed out so far over ALL launches on this matrix (never reset: every
+                                  // launch has exactly n_items CTAs and each takes one, so chunk = ticket % n_items)
     // Column-banded matrices (engine.cu, build_bands): a pass over the matrix is one launch per band; every band but the
     // last stores its row sums (+ those of the bands before it) in carry_out instead of running the epilogue, the last
     // band adds carry_in to its own row sums first.  Both null for an ordinary matrix.  Single-product ops only.
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     // The chunk this CTA works on comes from a ticket: chunks are handed out in the order CTAs START, so every item to
     // the left of ours belongs to a CTA that is already running (or done) -- the look-back below cannot wait for a CTA
     // that was never scheduled, whatever order the hardware dispatches blockIdx in.
-    if (threadIdx.x == 0) chunk_s = atomicAdd(M.ticket, 1u);
+    if (threadIdx.x == 0) chunk_s = (unsigned)(atomicAdd(M.ticket, 1ULL) % (unsigned long long)gridDim.x);
     if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
     const int chunk = (int)chunk_s;
@@ -353,11 +354,6 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
         if (lane == 0) complete_row(rA, sum, P0, P1);
     }
     if (!M.carry_out) op.finish(red_scratch, chunk);   // (warp-uniform: kernel argument); partials indexed by chunk: deterministic
-    // the last CTA to finish re-arms the ticket for the next launch over this matrix (launches are stream-ordered)
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(M.ticket + 1, 1u);
-        if (done == gridDim.x - 1) { M.ticket[0] = 0u; M.ticket[1] = 0u; }
-    }
 }
 
 // item_row[i] = first row finalised by warp item i = first r with rowPtr[r+1] > i*kWarpChunk (item 0 also owns

@@ -77,6 +77,7 @@ void fill_b200_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *inf
     info->norm_b_org = h.scal[4]; info->norm_c_org = h.scal[5];
     info->lanes_A = eng.A.G; info->lanes_AT = eng.AT.G; info->items_A = eng.A.n_items; info->items_AT = eng.AT.n_items;
     info->bands_A = (int)eng.A.bands.size(); info->reserved0 = eng.nranks;
+    info->peer_exchange = eng.px ? 1 : 0; info->reserved1 = 0;
 }
 
 namespace {
@@ -174,20 +175,29 @@ extern "C" int hprlp_b200_nccl_unique_id(char *out128) {
     });
 }
 
+extern "C" hprlp_b200_comm *hprlp_b200_comm_create(const char *uid128, int rank, int nranks, int device) {
+    return abi_guard<hprlp_b200_comm *>("hprlp_b200_comm_create", [&]() -> hprlp_b200_comm * {
+        if (!uid128 || nranks < 2 || rank < 0 || rank >= nranks) throw std::runtime_error("bad arguments");
+        std::unique_ptr<hprlp_b200_comm> c(new hprlp_b200_comm);
+        c->device = device;
+        c->coll.reset(open_nccl_rank(uid128, rank, nranks, device));
+        return c.release();
+    }, [] { return (hprlp_b200_comm *)nullptr; });
+}
+extern "C" void hprlp_b200_comm_destroy(hprlp_b200_comm *comm) { delete comm; }
+
 extern "C" HPRLP_results hprlp_b200_solve_partitioned_rank(const LP_info_cpu *model, const HPRLP_parameters *param_in,
-                                                            const char *uid128, int rank, int nranks, int quiet,
-                                                            hprlp_b200_info *info) {
+                                                            hprlp_b200_comm *comm, int quiet, hprlp_b200_info *info) {
     return abi_guard_results("hprlp_b200_solve_partitioned_rank", [&]() -> HPRLP_results {
         HPRLP_parameters def;
         const HPRLP_parameters param = param_in ? *param_in : def;
-        if (!model || !model->A || !uid128 || rank < 0 || rank >= nranks || nranks > model->m) {
+        if (!model || !model->A || !comm || !comm->coll || comm->coll->nranks > model->m) {
             abi_report("hprlp_b200_solve_partitioned_rank", "bad arguments");
             return abi_error_result();
         }
-        if (nranks == 1) return hprlp_b200_solve_ex(model, &param, nullptr, 0, nullptr, nullptr, nullptr, nullptr, quiet, info);
-        const std::vector<int> b = row_blocks_by_nnz(model->A->rowPtr, model->m, nranks);
-        std::unique_ptr<Collective> coll(open_nccl_rank(uid128, rank, nranks, param.device_number));
-        return solve_rank(model, b, rank, param.device_number, coll.get(), param, quiet != 0, info);
+        Collective *coll = comm->coll.get();
+        const std::vector<int> b = row_blocks_by_nnz(model->A->rowPtr, model->m, coll->nranks);
+        return solve_rank(model, b, coll->rank, comm->device, coll, param, quiet != 0, info);
     });
 }
 

@@ -251,18 +251,17 @@ extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, 
 // The same, one process per GPU: this process generates and owns row block `rank` of `nranks` (NCCL communicator from
 // the unique id the caller distributed, see hprlp_b200_nccl_unique_id).
 extern "C" HPRLP_results hprlp_b200_solve_partitioned_synth_rank(long long m, int n, int K, unsigned long long seed,
-                                                                  const HPRLP_parameters *param_in, const char *uid128, int rank,
-                                                                  int nranks, int quiet, int want_solution, double *obj_star,
+                                                                  const HPRLP_parameters *param_in, hprlp_b200_comm *comm,
+                                                                  int quiet, int want_solution, double *obj_star,
                                                                   hprlp_b200_info *info) {
     return abi_guard_results("hprlp_b200_solve_partitioned_synth_rank", [&]() -> HPRLP_results {
         HPRLP_parameters def;
         const HPRLP_parameters param = param_in ? *param_in : def;
-        if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !uid128)) throw std::runtime_error("synth rank: bad arguments");
+        Collective *coll = comm ? comm->coll.get() : nullptr;
+        const int nranks = coll ? coll->nranks : 1, rank = coll ? coll->rank : 0;
         const SynthSpec sp{m, n, K, seed};
         check_synth(sp, nranks);
-        std::unique_ptr<Collective> coll;
-        if (nranks > 1) coll.reset(open_nccl_rank(uid128, rank, nranks, param.device_number));
-        HPRLP_results out = synth_rank(sp, rank, nranks, param.device_number, coll.get(), param, quiet != 0, obj_star, info);
+        HPRLP_results out = synth_rank(sp, rank, nranks, comm ? comm->device : param.device_number, coll, param, quiet != 0, obj_star, info);
         if (!want_solution) { std::free(out.x); std::free(out.y); std::free(out.z); out.x = out.y = out.z = nullptr; }
         return out;
     });

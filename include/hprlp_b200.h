@@ -26,6 +26,8 @@ typedef struct {
     int items_A, items_AT;
     int bands_A;                    /* column bands of A (0 = single pass; >1 when n doubles exceed the L2 budget) */
     int reserved0;                  /* ranks of the row partition (1 = single GPU) */
+    int peer_exchange;              /* 1: per-iteration exchange = our fused kernel over NVLink peer memory; 0: NCCL collectives */
+    int reserved1;
 } hprlp_b200_info;
 
 /* HPRLP_main_solve with hooks.  power_z0 (host, length m) overrides the cuRAND start vector when
@@ -86,15 +88,18 @@ HPRLP_results hprlp_b200_solve_partitioned_local(const LP_info_cpu *model, const
                                                  int quiet, hprlp_b200_info *info);
 
 /* One process per GPU (torchrun / MPI style launch).  Rank 0 calls hprlp_b200_nccl_unique_id and distributes the 128
- * bytes (bench.py: torch.distributed broadcast); every rank then passes the FULL host model, the id, its rank and the
- * rank count; the rank uploads and owns its row block on device param->device_number.  All ranks return the full
- * solution.  hprlp_b200_engine_create_rank is the resident-engine variant (hprlp_b200_engine_run etc. are collective:
- * every rank calls them with the same arguments). */
+ * bytes (bench.py: torch.distributed broadcast); every rank creates ONE communicator handle for device `device` and
+ * reuses it for any number of partitioned solves (the NCCL bootstrap costs seconds, a solve tenths of a second).
+ * Every rank passes the FULL host model; the rank uploads and owns its row block.  All ranks return the full solution.
+ * hprlp_b200_engine_create_rank is the resident-engine variant (hprlp_b200_engine_run etc. are then collective: every
+ * rank calls them with the same arguments).  A communicator must outlive the engines created on it. */
+typedef struct hprlp_b200_comm hprlp_b200_comm;
 int hprlp_b200_nccl_unique_id(char *out128);
-HPRLP_results hprlp_b200_solve_partitioned_rank(const LP_info_cpu *model, const HPRLP_parameters *param, const char *uid128,
-                                                int rank, int nranks, int quiet, hprlp_b200_info *info);
-hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *model, const HPRLP_parameters *param,
-                                                 const char *uid128, int rank, int nranks);
+hprlp_b200_comm *hprlp_b200_comm_create(const char *uid128, int rank, int nranks, int device);
+void hprlp_b200_comm_destroy(hprlp_b200_comm *comm);
+HPRLP_results hprlp_b200_solve_partitioned_rank(const LP_info_cpu *model, const HPRLP_parameters *param, hprlp_b200_comm *comm,
+                                                int quiet, hprlp_b200_info *info);
+hprlp_b200_engine *hprlp_b200_engine_create_rank(const LP_info_cpu *model, const HPRLP_parameters *param, hprlp_b200_comm *comm);
 
 /* Diagnostic: ms of one in-place reduce-scatter + all-gather pair (out_ms[0]) and of one all-reduce (out_ms[1]) of
  * `count` doubles over n_gpus GPUs, issued exactly as the partitioned solver issues them.  Returns 0 on success. */
@@ -109,7 +114,7 @@ HPRLP_results hprlp_b200_solve_partitioned_synth(long long m, int n, int K, unsi
                                                  double *obj_star, hprlp_b200_info *info);
 /* The same with one process per GPU (see hprlp_b200_solve_partitioned_rank): this process generates row block `rank`. */
 HPRLP_results hprlp_b200_solve_partitioned_synth_rank(long long m, int n, int K, unsigned long long seed,
-                                                      const HPRLP_parameters *param, const char *uid128, int rank, int nranks,
+                                                      const HPRLP_parameters *param, hprlp_b200_comm *comm,
                                                       int quiet, int want_solution, double *obj_star, hprlp_b200_info *info);
 /* Test hook: rows [row0, row0+rows) of that matrix, generated on the device, copied to host (rows*K entries each). */
 int hprlp_b200_synth_rows(int n, int K, unsigned long long seed, long long row0, int rows, int *col_out, double *val_out);

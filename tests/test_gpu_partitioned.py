@@ -15,10 +15,14 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("kind,m,n,nnz", [("uniform", 3000, 9000, 90000), ("powerlaw", 20000, 50000, 1000000)])
-def test_partitioned_matches_single_gpu(pkg, engine, kind, m, n, nnz):
+def test_partitioned_matches_single_gpu(pkg, engine, kind, m, n, nnz, exchange, monkeypatch):
+    """exchange = p2p: our fused reduce-scatter + x-update + all-gather kernel over NVLink peer memory;
+    nccl: ncclReduceScatter + x-update kernel + ncclAllGather."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    monkeypatch.setenv("HPRLP_EXCHANGE", exchange)
     lp = pkg.synth_lp(kind, m, n, nnz, with_solution=True)
     for prm in (dict(stop_tol=1e-6), dict(max_iter=300, stop_tol=1e-30)):
         p = pkg.Parameters.default(use_presolve=False, **prm)
@@ -26,6 +30,7 @@ def test_partitioned_matches_single_gpu(pkg, engine, kind, m, n, nnz):
         one = engine.solve(model, p, main=True)
         two = engine.solve_partitioned(model, p, n_gpus=2)
         engine.free_model(model)
+        assert two["info"]["peer_exchange"] == (1 if exchange == "p2p" else 0)
         assert one["status"] == two["status"] and one["iter"] == two["iter"], (prm, one["iter"], two["iter"])
         assert abs(one["primal_obj"] - two["primal_obj"]) <= 1e-9 * (1 + abs(one["primal_obj"]))
         for k in "xyz":
