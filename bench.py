@@ -153,6 +153,11 @@ class Quiet:
 
 
 def dist_setup(n_gpus):
+    with Quiet():     # NCCL announces its version on stdout when the first communicator comes up
+        return _dist_setup(n_gpus)
+
+
+def _dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,6 +168,7 @@ def dist_setup(n_gpus):
         torch.cuda.set_device(local)
         dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
+        dist.barrier(device_ids=[local])
     return rank, world, local, dist
 
 

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -52,6 +53,24 @@ struct BView {
     const double *val;
 };
 
+// L2 residency policy of the batched passes (north_star: "gathered vectors staged through ... L2-persisting windows").
+// The gathered operand of a pass (one [row][32] slab per group: 12.8 MB for Y, 51 MB for X_hat on configs[3]) is re-read
+// ~nnz/rows times and must stay in the 126 MB L2; everything else is touched once per pass.  So gathers are loaded with
+// evict_last priority and the per-row vectors with evict_first / streaming stores.  Without the hints the streamed
+// vectors evict the slab: ncu on r1 showed a 47 % L2 hit rate and 3.4x the algorithmic DRAM reads in the y-phase.
+__device__ __forceinline__ unsigned long long make_keep_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_keep(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_once(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_once(double *p, double v) { __stcs(p, v); }
+
 // ---------------------------------------------------------------------------------------------
 // skeleton: one warp per row, lane = instance of group blockIdx.y
 // ---------------------------------------------------------------------------------------------
@@ -62,6 +81,7 @@ __global__ void __launch_bounds__(kBThreads) batched_rows_kernel(BView M, Op op)
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     op.init(g, lane);
+    const unsigned long long keep = make_keep_policy();
     const int row0 = blockIdx.x * kRowsPerCta;
     const int row1 = min(M.rows, row0 + kRowsPerCta);
     const size_t gbase = (size_t)g * M.gcols;
@@ -79,7 +99,7 @@ __global__ void __launch_bounds__(kBThreads) batched_rows_kernel(BView M, Op op)
             for (int t = 0; t < cnt; ++t) {
                 const int cc = __shfl_sync(0xffffffffu, c, t);
                 const double vv = __shfl_sync(0xffffffffu, v, t);
-                op.accum(vv, (gbase + cc) * kGS + lane, acc);
+                op.accum(vv, (gbase + cc) * kGS + lane, acc, keep);
             }
         }
         op.row(r, ((size_t)g * M.rows + r) * kGS + lane, acc);
@@ -141,20 +161,20 @@ struct BXOp : BOpBase {
         f2 = 1.0 - f1;
         if (blockIdx.x == 0 && threadIdx.x < 32) ky[inst] = k;
     }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(Y + gi), acc[0]); }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(Y + gi, keep), acc[0]); }
     __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
         if (!on) return;
-        const double xi = X[t];
-        const double zt = fma(sig, acc[0] - C[t], xi);
-        const double xb = fmin(fmax(zt, L[t]), U[t]);
+        const double xi = ld_once(X + t);
+        const double zt = fma(sig, acc[0] - ld_once(C + t), xi);
+        const double xb = fmin(fmax(zt, ld_once(L + t)), ld_once(U + t));
         const double xh = 2.0 * xb - xi;
         if (CHECK) {
-            DX[t] = xb - xh;
-            Z_bar[t] = (xb - zt) / sig;
-            X_bar[t] = xb;
+            st_once(DX + t, xb - xh);
+            st_once(Z_bar + t, (xb - zt) / sig);
+            st_once(X_bar + t, xb);
         }
-        X_hat[t] = xh;
-        X[t] = fma(f2, xh, f1 * lastX[t]);
+        X_hat[t] = xh;   // gathered by the y-phase that follows: normal priority
+        st_once(X + t, fma(f2, xh, f1 * ld_once(lastX + t)));
     }
 };
 
@@ -182,20 +202,20 @@ struct BYOp : BOpBase {
         f2 = 1.0 - f1;
         if (blockIdx.x == 0 && threadIdx.x < 32 && on) kx[inst] = k + 1;
     }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(X_hat + gi), acc[0]); }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(X_hat + gi, keep), acc[0]); }
     __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
         if (!on) return;
-        const double yi = Y[t];
+        const double yi = ld_once(Y + t);
         const double v = fma(-fact1, yi, acc[0]);
-        const double d = fmax(AL[t] - v, fmin(AU[t] - v, 0.0));
+        const double d = fmax(ld_once(AL + t) - v, fmin(ld_once(AU + t) - v, 0.0));
         const double yb = d / fact1;
         const double yh = 2.0 * yb - yi;
         if (CHECK) {
-            DY[t] = yb - yh;
-            Y_bar[t] = yb;
-            Y_obj[t] = v + d;
+            st_once(DY + t, yb - yh);
+            st_once(Y_bar + t, yb);
+            st_once(Y_obj + t, v + d);
         }
-        Y[t] = fma(f2, yh, f1 * lastY[t]);
+        Y[t] = fma(f2, yh, f1 * ld_once(lastY + t));   // gathered by the next x-phase: normal priority
     }
 };
 
@@ -207,7 +227,7 @@ struct BResDualOp : BOpBase {
     double *partials;
     double t[4];
     __device__ __forceinline__ void init(int, int) { t[0] = t[1] = t[2] = t[3] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(Y_bar + gi), acc[0]); }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(Y_bar + gi, keep), acc[0]); }
     __device__ __forceinline__ void row(int j, size_t i, const double (&acc)[1]) {
         const double cj = C[i], zb = Z_bar[i], xb = X_bar[i], cn = col_norm[j];
         const double rd = (cj - acc[0] - zb) * cn;
@@ -232,7 +252,7 @@ struct BResPrimalOp : BOpBase {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(X_bar + gi), acc[0]); }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(X_bar + gi, keep), acc[0]); }
     __device__ __forceinline__ void row(int r, size_t i, const double (&acc)[1]) {
         const double ax = acc[0];
         const double rp = row_norm[r] * fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax);
@@ -250,7 +270,7 @@ struct BWeightedOp : BOpBase {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1]) const { acc[0] = fma(v, __ldg(DX + gi), acc[0]); }
+    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(DX + gi, keep), acc[0]); }
     __device__ __forceinline__ void row(int, size_t i, const double (&acc)[1]) {
         const double dy = DY[i];
         t[0] += acc[0] * dy;
@@ -302,20 +322,6 @@ __global__ void __launch_bounds__(kBThreads) batched_restart_kernel(const double
 }
 
 // column-major host layout (instance k, row i at k*rows + i) <-> device layout [g][i][32]
-__global__ void to_group_layout_kernel(const double *src, double *dst, int rows, int B, double pad) {
-    __shared__ double tile[32][33];
-    const int g = blockIdx.y, r0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (int k = ty; k < 32; k += 8) {
-        const int inst = g * kGS + k, r = r0 + tx;
-        tile[k][tx] = (inst < B && r < rows) ? src[(size_t)inst * rows + r] : pad;
-    }
-    __syncthreads();
-    for (int k = ty; k < 32; k += 8) {
-        const int r = r0 + k;
-        if (r < rows) dst[((size_t)g * rows + r) * kGS + tx] = tile[tx][k];
-    }
-}
 // device layout -> column-major with unscaling: out = (v (/|*) norm[row]) * scale[instance]
 // (reference collect_results :915-924)
 template <bool DIVIDE>
@@ -338,38 +344,176 @@ __global__ void from_group_layout_kernel(const double *src, double *dst, int row
     }
 }
 
-template <typename T>
-T *balloc(size_t count) {
-    T *p = nullptr;
-    HPR_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-    HPR_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
-    // cudaMemset runs on the legacy default stream and is asynchronous for device memory; the engine's streams are
-    // non-blocking, so without this barrier a later kernel could be overtaken by the zero-fill.
-    HPR_CUDA_CHECK(cudaDeviceSynchronize());
+// ---------------------------------------------------------------------------------------------
+// per-instance scaling on the DEVICE (reference build_batched_lp_device, src/batched_solver.cu:792-885, runs these
+// loops on the host, one instance after the other).  The inputs arrive column-major (instance k, row i at k*rows + i),
+// exactly as the caller holds them; every elementwise operation is the reference's (same divisions, same order, two
+// separately rounded steps).  The reference accumulates its norms in long double (:332-354); here they are accumulated
+// in double-double (error-free products and sums, ~106 bits) in a fixed order, i.e. at least as accurately, and rounded
+// to double once -- the result can differ from the reference's by one ulp of the norm when its own 64-bit accumulation
+// error crosses a rounding boundary.
+// ---------------------------------------------------------------------------------------------
+struct DD { double hi, lo; };
+__device__ __forceinline__ DD dd_add(DD a, DD b) {
+    const double s = a.hi + b.hi;
+    const double bb = s - a.hi;
+    const double e = (a.hi - (s - bb)) + (b.hi - bb);
+    const double t = e + (a.lo + b.lo);
+    const double hi = s + t;
+    return DD{hi, t - (hi - s)};
+}
+__device__ __forceinline__ DD dd_add_sq(DD a, double v) {
+    const double p = v * v;
+    return dd_add(a, DD{p, fma(v, v, -p)});
+}
+__device__ __forceinline__ double bound_abs(double lo, double hi) {   // reference bound_norm_host :332-343
+    const double a = (isinf(lo) && lo < 0) ? 0.0 : fabs(lo);
+    const double b = (isinf(hi) && hi > 0) ? 0.0 : fabs(hi);
+    return fmax(a, b);
+}
+constexpr int kNormChunks = 32;   // CTAs per instance in the norm passes
+// fixed-order CTA reduction of NS double-double accumulators; thread 0 writes partial[(inst*kNormChunks + chunk)*NS + s]
+template <int NS>
+__device__ __forceinline__ void dd_block_store(DD (&acc)[NS], DD *partial) {
+    __shared__ DD sm[NS][kBWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        DD v = acc[s];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            DD o;
+            o.hi = __shfl_xor_sync(0xffffffffu, v.hi, off);
+            o.lo = __shfl_xor_sync(0xffffffffu, v.lo, off);
+            v = dd_add(v, o);
+        }
+        if (lane == 0) sm[s][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            DD v = sm[s][0];
+            for (int w = 1; w < kBWarps; ++w) v = dd_add(v, sm[s][w]);
+            partial[((size_t)blockIdx.y * kNormChunks + blockIdx.x) * NS + s] = v;
+        }
+    }
+}
+// rows: slot 0 |b|^2 of the raw bounds, then AL,AU /= row_norm in place, slot 1 |b|^2 of the scaled bounds
+__global__ void __launch_bounds__(kBThreads) batched_scale_rows_kernel(double *AL, double *AU, const double *row_norm, int m, DD *partial) {
+    const size_t base = (size_t)blockIdx.y * m;
+    DD acc[2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += kNormChunks * blockDim.x) {
+        double lo = AL[base + i], hi = AU[base + i];
+        acc[0] = dd_add_sq(acc[0], bound_abs(lo, hi));
+        const double rn = row_norm[i];
+        lo = lo / rn; hi = hi / rn;
+        AL[base + i] = lo; AU[base + i] = hi;
+        acc[1] = dd_add_sq(acc[1], bound_abs(lo, hi));
+    }
+    dd_block_store<2>(acc, partial);
+}
+// columns: slot 0 |c|^2 raw, then C /= col_norm in place, slot 1 |c|^2 scaled
+__global__ void __launch_bounds__(kBThreads) batched_scale_cols_kernel(double *Cm, const double *col_norm, int n, DD *partial) {
+    const size_t base = (size_t)blockIdx.y * n;
+    DD acc[2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += kNormChunks * blockDim.x) {
+        double c = Cm[base + i];
+        acc[0] = dd_add_sq(acc[0], c);
+        c = c / col_norm[i];
+        Cm[base + i] = c;
+        acc[1] = dd_add_sq(acc[1], c);
+    }
+    dd_block_store<2>(acc, partial);
+}
+// second pass (bounds/cost scaling): divide by the instance's scale in place (if on), slot 0 = norm^2 of the result
+__global__ void __launch_bounds__(kBThreads) batched_div_rows_kernel(double *AL, double *AU, const double *scale, bool on, int m, DD *partial) {
+    const size_t base = (size_t)blockIdx.y * m;
+    const double sc = scale[blockIdx.y];
+    DD acc[1] = {{0.0, 0.0}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += kNormChunks * blockDim.x) {
+        double lo = AL[base + i], hi = AU[base + i];
+        if (on) { lo = lo / sc; hi = hi / sc; AL[base + i] = lo; AU[base + i] = hi; }
+        acc[0] = dd_add_sq(acc[0], bound_abs(lo, hi));
+    }
+    dd_block_store<1>(acc, partial);
+}
+__global__ void __launch_bounds__(kBThreads) batched_div_cols_kernel(double *Cm, const double *scale, bool on, int n, DD *partial) {
+    const size_t base = (size_t)blockIdx.y * n;
+    const double sc = scale[blockIdx.y];
+    DD acc[1] = {{0.0, 0.0}};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += kNormChunks * blockDim.x) {
+        double c = Cm[base + i];
+        if (on) { c = c / sc; Cm[base + i] = c; }
+        acc[0] = dd_add_sq(acc[0], c);
+    }
+    dd_block_store<1>(acc, partial);
+}
+// out[s][k] = sqrt(sum over the instance's chunks, in chunk order) (+ 1 where plus_one[s]); on == false: out = 1
+__global__ void batched_norm_finalize_kernel(const DD *partial, int ns, int B, int Bpad, double *out, int plus_one_mask, int skip_mask) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B) return;
+    for (int s = 0; s < ns; ++s) {
+        DD v = partial[((size_t)k * kNormChunks) * ns + s];
+        for (int c = 1; c < kNormChunks; ++c) v = dd_add(v, partial[((size_t)k * kNormChunks + c) * ns + s]);
+        double r = sqrt(v.hi + v.lo);
+        if (plus_one_mask & (1 << s)) r = 1.0 + r;
+        if (skip_mask & (1 << s)) r = 1.0;
+        out[(size_t)s * Bpad + k] = r;
+    }
+}
+// column-major -> [g][row][32] with the last elementwise steps fused:
+//   COLSCALE (l, u): v *= col_norm[row], then (bc) v /= b_scale[instance]          (reference :835-847)
+//   REPL -1: -inf -> -1e100 (AL, l);  +1: +inf -> +1e100 (AU, u);  0: none (C)      (reference :849-864)
+template <int REPL, bool COLSCALE>
+__global__ void to_group_layout_scaled_kernel(const double *src, double *dst, int rows, int B, const double *col_norm,
+                                              const double *b_scale, bool bc) {
+    __shared__ double tile[32][33];
+    const int g = blockIdx.y, r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int inst = g * kGS + k, r = r0 + tx;
+        double v = 0.0;
+        if (inst < B && r < rows) {
+            v = src[(size_t)inst * rows + r];
+            if (COLSCALE) {
+                v = v * col_norm[r];
+                if (bc) v = v / b_scale[inst];
+            }
+            if (REPL < 0 && isinf(v) && v < 0) v = -kInfReplacement;
+            if (REPL > 0 && isinf(v) && v > 0) v = kInfReplacement;
+        }
+        tile[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int r = r0 + k;
+        if (r < rows) dst[((size_t)g * rows + r) * kGS + tx] = tile[tx][k];
+    }
+}
+
+// pinned host blocks recycled for the life of the process (cudaFreeHost synchronises the device: engine.cu)
+std::mutex g_bpin_mu;
+std::vector<std::pair<double *, size_t>> g_bpin_free;
+double *bpinned_acquire(size_t doubles) {
+    {
+        std::lock_guard<std::mutex> lk(g_bpin_mu);
+        for (size_t i = 0; i < g_bpin_free.size(); ++i)
+            if (g_bpin_free[i].second >= doubles) { double *p = g_bpin_free[i].first; g_bpin_free.erase(g_bpin_free.begin() + i); return p; }
+    }
+    double *p = nullptr;
+    HPR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&p), sizeof(double) * doubles, cudaHostAllocPortable));
     return p;
+}
+void bpinned_release(double *p, size_t doubles) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_bpin_mu);
+    g_bpin_free.emplace_back(p, doubles);
 }
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int step_of(int iter) { return std::max(10, static_cast<int>(pow(10, floor(log10((double)iter))) / 10)); }
-
-// reference bound_norm_host / column_norm_host (:332-354): long-double accumulation on the host
-double bound_norm_host(const double *AL, const double *AU, int m) {
-    long double sum = 0.0;
-    for (int i = 0; i < m; ++i) {
-        const double lo = AL[i], hi = AU[i];
-        const double a = std::isinf(lo) && lo < 0 ? 0.0 : std::abs(lo);
-        const double b = std::isinf(hi) && hi > 0 ? 0.0 : std::abs(hi);
-        const double v = std::max(a, b);
-        sum += static_cast<long double>(v) * v;
-    }
-    return std::sqrt(static_cast<double>(sum));
-}
-double column_norm_host(const double *X, int n) {
-    long double sum = 0.0;
-    for (int i = 0; i < n; ++i) sum += static_cast<long double>(X[i]) * X[i];
-    return std::sqrt(static_cast<double>(sum));
-}
 
 HPRLP_batched_results make_batched_error(const char *status, int m, int n, int B) {   // reference :356-368
     HPRLP_batched_results r;
@@ -408,28 +552,23 @@ class BatchedSolver {
     int nbx_A = 0, nbx_AT = 0, nbx_vec = 0;
     long long launches = 0;
     std::vector<double> b_scale, c_scale, norm_b, norm_c, norm_b_org, norm_c_org, obj_constants;
-    std::vector<double> row_norm_h, col_norm_h;
+
+    void *arena = nullptr;       // one block of the engines' pool behind every device array below
+    size_t h_scal_doubles = 0;
+    DD *d_dd = nullptr;          // double-double partials of the setup norms
+    double *d_stage2 = nullptr;  // second / third column-major staging buffers (m * B each) for AL, AU
+    double *d_stage3 = nullptr;
+    double *d_norms = nullptr;   // [6][Bpad]: norm_b_org, b_scale, norm_c_org, c_scale, norm_b, norm_c
 
     ~BatchedSolver() {
-        for (void *p : {(void *)X, (void *)X_hat, (void *)X_bar, (void *)DX, (void *)Z_bar, (void *)lastX, (void *)C, (void *)L, (void *)U,
-                        (void *)Y, (void *)Y_bar, (void *)DY, (void *)Y_obj, (void *)lastY, (void *)AL, (void *)AU, (void *)d_sigma,
-                        (void *)d_scale_b, (void *)d_scale_c, (void *)d_k, (void *)d_active, (void *)d_flags, (void *)d_partials,
-                        (void *)d_scal, (void *)d_stage})
-            if (p) cudaFree(p);
-        if (h_scal) cudaFreeHost(h_scal);
+        if (arena) pool_free(arena, stream);
+        bpinned_release(h_scal, h_scal_doubles);
     }
 
     BView viewA() const { return BView{m, n, eng.A.rowPtr, eng.A.col, eng.A.val}; }
     BView viewAT() const { return BView{n, m, eng.AT.rowPtr, eng.AT.col, eng.AT.val}; }
     dim3 gridA() const { return dim3(nbx_A, G); }
     dim3 gridAT() const { return dim3(nbx_AT, G); }
-
-    void upload_dense(const double *host, double *dst, int rows, double pad) {
-        HPR_CUDA_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * (size_t)rows * B, cudaMemcpyHostToDevice, stream));
-        to_group_layout_kernel<<<dim3((rows + 31) / 32, G), 256, 0, stream>>>(d_stage, dst, rows, B, pad);
-        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // staging buffer is reused
-        launches++;
-    }
 
     void fetch(int slots) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * (size_t)slots * Bpad, cudaMemcpyDeviceToHost, stream));
@@ -567,65 +706,92 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         S.eng.scale(&mp);
     }
     S.stream = S.eng.stream;
-    S.row_norm_h.resize(m); S.col_norm_h.resize(n);
-    HPR_CUDA_CHECK(cudaMemcpy(S.row_norm_h.data(), S.eng.row_norm, sizeof(double) * m, cudaMemcpyDeviceToHost));
-    HPR_CUDA_CHECK(cudaMemcpy(S.col_norm_h.data(), S.eng.col_norm, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaStream_t st = S.stream;
+    const bool bc = actual.use_bc_scaling;
+    static const bool timing = getenv("HPRLP_TIMING") != nullptr;   // stage wall times on stderr
+    double t_mark = now_s();
+    auto stage_done = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const double t = now_s();
+        std::fprintf(stderr, "[hprlp timing] batched %s %.4f s\n", what, t - t_mark);
+        t_mark = t;
+    };
+    stage_done("matrix upload + scaling");
 
-    // per-instance scaling on the host -- reference build_batched_lp_device :792-885
-    std::vector<double> hC(C_in, C_in + (size_t)n * B), hAL(AL_in, AL_in + (size_t)m * B), hAU(AU_in, AU_in + (size_t)m * B);
-    std::vector<double> hL(l_in, l_in + (size_t)n * B), hU(u_in, u_in + (size_t)n * B);
-    S.b_scale.assign(B, 1.0); S.c_scale.assign(B, 1.0); S.norm_b.assign(B, 0.0); S.norm_c.assign(B, 0.0);
-    S.norm_b_org.assign(B, 1.0); S.norm_c_org.assign(B, 1.0);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int k = 0; k < B; ++k) {
-        double *al = hAL.data() + (size_t)k * m, *au = hAU.data() + (size_t)k * m;
-        double *cc = hC.data() + (size_t)k * n, *ll = hL.data() + (size_t)k * n, *uu = hU.data() + (size_t)k * n;
-        S.norm_b_org[k] = 1.0 + bound_norm_host(al, au, m);
-        S.norm_c_org[k] = 1.0 + column_norm_host(cc, n);
-        for (int i = 0; i < m; ++i) { const double rn = S.row_norm_h[i]; al[i] /= rn; au[i] /= rn; }
-        for (int i = 0; i < n; ++i) { const double cn = S.col_norm_h[i]; cc[i] /= cn; ll[i] *= cn; uu[i] *= cn; }
-        if (actual.use_bc_scaling) {
-            S.b_scale[k] = 1.0 + bound_norm_host(al, au, m);
-            S.c_scale[k] = 1.0 + column_norm_host(cc, n);
-            for (int i = 0; i < m; ++i) { al[i] /= S.b_scale[k]; au[i] /= S.b_scale[k]; }
-            for (int i = 0; i < n; ++i) { cc[i] /= S.c_scale[k]; ll[i] /= S.b_scale[k]; uu[i] /= S.b_scale[k]; }
-        }
-        S.norm_b[k] = bound_norm_host(al, au, m);
-        S.norm_c[k] = column_norm_host(cc, n);
-        for (int i = 0; i < m; ++i) {
-            if (std::isinf(al[i]) && al[i] < 0) al[i] = -kInfReplacement;
-            if (std::isinf(au[i]) && au[i] > 0) au[i] = kInfReplacement;
-        }
-        for (int i = 0; i < n; ++i) {
-            if (std::isinf(ll[i]) && ll[i] < 0) ll[i] = -kInfReplacement;
-            if (std::isinf(uu[i]) && uu[i] > 0) uu[i] = kInfReplacement;
-        }
-    }
-    S.obj_constants.assign(B, model->obj_constant);
-    if (obj_constants) S.obj_constants.assign(obj_constants, obj_constants + B);
-
-    // device state
+    // device state: one zero-filled block of the engines' pool, carved into the arrays
     const size_t nG = (size_t)n * S.Bpad, mG = (size_t)m * S.Bpad;
-    S.X = balloc<double>(nG); S.X_hat = balloc<double>(nG); S.X_bar = balloc<double>(nG); S.DX = balloc<double>(nG);
-    S.Z_bar = balloc<double>(nG); S.lastX = balloc<double>(nG); S.C = balloc<double>(nG); S.L = balloc<double>(nG); S.U = balloc<double>(nG);
-    S.Y = balloc<double>(mG); S.Y_bar = balloc<double>(mG); S.DY = balloc<double>(mG); S.Y_obj = balloc<double>(mG);
-    S.lastY = balloc<double>(mG); S.AL = balloc<double>(mG); S.AU = balloc<double>(mG);
-    S.d_sigma = balloc<double>(S.Bpad); S.d_scale_b = balloc<double>(S.Bpad); S.d_scale_c = balloc<double>(S.Bpad);
-    S.d_k = balloc<int>(2 * (size_t)S.Bpad);
-    S.d_active = balloc<unsigned char>(S.Bpad); S.d_flags = balloc<unsigned char>(S.Bpad);
     S.nbx_A = (m + kRowsPerCta - 1) / kRowsPerCta;
     S.nbx_AT = (n + kRowsPerCta - 1) / kRowsPerCta;
     S.nbx_vec = std::max(1, std::min((std::max(m, n) + kBWarps - 1) / kBWarps, 148 * 2));
     const size_t nblk = (size_t)std::max(std::max(S.nbx_A, S.nbx_AT), S.nbx_vec) * S.G;
-    S.d_partials = balloc<double>(nblk * kMaxSlots * kGS);
-    S.d_scal = balloc<double>((size_t)kMaxSlots * S.Bpad);
-    HPR_CUDA_CHECK(cudaMallocHost(&S.h_scal, sizeof(double) * kMaxSlots * S.Bpad));
-    S.d_stage = balloc<double>((size_t)std::max(m, n) * B);
-    S.upload_dense(hC.data(), S.C, n, 0.0);
-    S.upload_dense(hL.data(), S.L, n, 0.0);
-    S.upload_dense(hU.data(), S.U, n, 0.0);
-    S.upload_dense(hAL.data(), S.AL, m, 0.0);
-    S.upload_dense(hAU.data(), S.AU, m, 0.0);
+    {
+        auto up = [](size_t b) { return (b + 511) & ~(size_t)511; };
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off += up(bytes); return o; };
+        const size_t o_n[9] = {take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8), take(nG * 8)};
+        const size_t o_m[7] = {take(mG * 8), take(mG * 8), take(mG * 8), take(mG * 8), take(mG * 8), take(mG * 8), take(mG * 8)};
+        const size_t o_sigma = take(S.Bpad * 8), o_sb = take(S.Bpad * 8), o_sc = take(S.Bpad * 8), o_k = take(2 * (size_t)S.Bpad * 4);
+        const size_t o_act = take(S.Bpad), o_flg = take(S.Bpad);
+        const size_t o_part = take(nblk * kMaxSlots * kGS * 8), o_scal = take((size_t)kMaxSlots * S.Bpad * 8);
+        const size_t o_stage = take((size_t)n * B * 8), o_stage2 = take((size_t)m * B * 8), o_stage3 = take((size_t)m * B * 8);
+        const size_t o_dd = take((size_t)B * kNormChunks * 2 * sizeof(DD)), o_norms = take((size_t)6 * S.Bpad * 8);
+        char *base = static_cast<char *>(pool_alloc_zeroed(off, actual.device_number, st));
+        S.arena = base;
+        double **nv[9] = {&S.X, &S.X_hat, &S.X_bar, &S.DX, &S.Z_bar, &S.lastX, &S.C, &S.L, &S.U};
+        for (int i = 0; i < 9; ++i) *nv[i] = reinterpret_cast<double *>(base + o_n[i]);
+        double **mv[7] = {&S.Y, &S.Y_bar, &S.DY, &S.Y_obj, &S.lastY, &S.AL, &S.AU};
+        for (int i = 0; i < 7; ++i) *mv[i] = reinterpret_cast<double *>(base + o_m[i]);
+        S.d_sigma = reinterpret_cast<double *>(base + o_sigma); S.d_scale_b = reinterpret_cast<double *>(base + o_sb);
+        S.d_scale_c = reinterpret_cast<double *>(base + o_sc); S.d_k = reinterpret_cast<int *>(base + o_k);
+        S.d_active = reinterpret_cast<unsigned char *>(base + o_act); S.d_flags = reinterpret_cast<unsigned char *>(base + o_flg);
+        S.d_partials = reinterpret_cast<double *>(base + o_part); S.d_scal = reinterpret_cast<double *>(base + o_scal);
+        S.d_stage = reinterpret_cast<double *>(base + o_stage); S.d_stage2 = reinterpret_cast<double *>(base + o_stage2);
+        S.d_stage3 = reinterpret_cast<double *>(base + o_stage3);
+        S.d_dd = reinterpret_cast<DD *>(base + o_dd); S.d_norms = reinterpret_cast<double *>(base + o_norms);
+    }
+    S.h_scal_doubles = (size_t)kMaxSlots * S.Bpad;
+    S.h_scal = bpinned_acquire(S.h_scal_doubles);
+
+    stage_done("state allocation");
+    // per-instance scaling on the device -- reference build_batched_lp_device :792-885.  Inputs are staged straight from
+    // the caller's (pageable) arrays by several host threads; no host copies, no host loops over B x (n + m) entries.
+    const dim3 norm_grid(kNormChunks, B);
+    const dim3 tgrid_n((n + 31) / 32, S.G), tgrid_m((m + 31) / 32, S.G);
+    double *dn = S.d_norms;   // rows of Bpad: 0 norm_b_org, 1 b_scale, 2 norm_c_org, 3 c_scale, 4 norm_b, 5 norm_c
+    // rows first: b_scale is needed by l and u
+    h2d_large(S.d_stage2, AL_in, sizeof(double) * (size_t)m * B, st);
+    h2d_large(S.d_stage3, AU_in, sizeof(double) * (size_t)m * B, st);
+    batched_scale_rows_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage2, S.d_stage3, S.eng.row_norm, m, S.d_dd);
+    batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 2, B, S.Bpad, dn, 0x3, bc ? 0 : 0x2);
+    batched_div_rows_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage2, S.d_stage3, dn + S.Bpad, bc, m, S.d_dd);
+    batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 1, B, S.Bpad, dn + 4 * (size_t)S.Bpad, 0, 0);
+    to_group_layout_scaled_kernel<-1, false><<<tgrid_m, 256, 0, st>>>(S.d_stage2, S.AL, m, B, nullptr, nullptr, false);
+    to_group_layout_scaled_kernel<1, false><<<tgrid_m, 256, 0, st>>>(S.d_stage3, S.AU, m, B, nullptr, nullptr, false);
+    // cost
+    h2d_large(S.d_stage, C_in, sizeof(double) * (size_t)n * B, st);
+    batched_scale_cols_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage, S.eng.col_norm, n, S.d_dd);
+    batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 2, B, S.Bpad, dn + 2 * (size_t)S.Bpad, 0x3, bc ? 0 : 0x2);
+    batched_div_cols_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage, dn + 3 * (size_t)S.Bpad, bc, n, S.d_dd);
+    batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 1, B, S.Bpad, dn + 5 * (size_t)S.Bpad, 0, 0);
+    to_group_layout_scaled_kernel<0, false><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.C, n, B, nullptr, nullptr, false);
+    // bounds on x: l, u *= col_norm, /= b_scale, +-inf -> +-1e100
+    h2d_large(S.d_stage, l_in, sizeof(double) * (size_t)n * B, st);
+    to_group_layout_scaled_kernel<-1, true><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.L, n, B, S.eng.col_norm, dn + S.Bpad, bc);
+    h2d_large(S.d_stage, u_in, sizeof(double) * (size_t)n * B, st);
+    to_group_layout_scaled_kernel<1, true><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.U, n, B, S.eng.col_norm, dn + S.Bpad, bc);
+    S.launches += 13;
+    {
+        std::vector<double> hn((size_t)6 * S.Bpad);
+        HPR_CUDA_CHECK(cudaMemcpyAsync(hn.data(), dn, sizeof(double) * hn.size(), cudaMemcpyDeviceToHost, st));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(st));
+        HPR_CUDA_CHECK(cudaGetLastError());
+        auto rowk = [&](int r) { return std::vector<double>(hn.begin() + (size_t)r * S.Bpad, hn.begin() + (size_t)r * S.Bpad + B); };
+        S.norm_b_org = rowk(0); S.b_scale = rowk(1); S.norm_c_org = rowk(2); S.c_scale = rowk(3); S.norm_b = rowk(4); S.norm_c = rowk(5);
+    }
+    S.obj_constants.assign(B, model->obj_constant);
+    if (obj_constants) S.obj_constants.assign(obj_constants, obj_constants + B);
+    stage_done("instance upload + scaling");
 
     // power iteration on the shared, scaled matrix -- reference :994-1001
     const double power_start = now_s();
@@ -648,6 +814,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     HPR_CUDA_CHECK(cudaMemcpy(S.d_scale_c, cs_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice));
     HPR_CUDA_CHECK(cudaMemcpy(S.d_active, act_pad.data(), S.Bpad, cudaMemcpyHostToDevice));
     const double setup_time = now_s() - setup_start;
+    stage_done("power iteration + scalars");
 
     const double solve_start = now_s();
     ResidualHost res;
@@ -749,6 +916,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     }
     HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
     const double solve_time = now_s() - solve_start;
+    stage_done("loop");
 
     // collect_results (reference :887-935): unscale on the device, one D2H per output array
     HPRLP_batched_results out;
@@ -764,8 +932,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     auto download = [&](const double *src, double *dst, int rows, bool divide, const double *norm, const double *scale) {
         if (divide) from_group_layout_kernel<true><<<dim3((rows + 31) / 32, S.G), 256, 0, S.stream>>>(src, S.d_stage, rows, B, norm, scale);
         else from_group_layout_kernel<false><<<dim3((rows + 31) / 32, S.G), 256, 0, S.stream>>>(src, S.d_stage, rows, B, norm, scale);
-        HPR_CUDA_CHECK(cudaMemcpyAsync(dst, S.d_stage, sizeof(double) * (size_t)rows * B, cudaMemcpyDeviceToHost, S.stream));
-        HPR_CUDA_CHECK(cudaStreamSynchronize(S.stream));
+        d2h_large(dst, S.d_stage, sizeof(double) * (size_t)rows * B, S.stream);
     };
     download(S.X_bar, out.x, n, true, S.eng.col_norm, S.d_scale_b);
     download(S.Z_bar, out.z, n, false, S.eng.col_norm, S.d_scale_c);
@@ -781,6 +948,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     out.solve_time = solve_time;
     out.power_time = power_time;
     out.time = setup_time + solve_time;
+    stage_done("collect results");
     return out;
 }
 

@@ -248,11 +248,18 @@ __global__ void exchange_signal_kernel(PeerPtrs pp, int P, int rank, int slot, u
 __global__ void exchange_wait_kernel(const unsigned long long *flags, int P, int slot, unsigned long long epoch) {
     if ((int)threadIdx.x < P) wait_epoch(flags + slot * kMaxPeers + threadIdx.x, epoch);
 }
+__device__ __forceinline__ double2 ld_peer2(const double *p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 // reduce-scatter + x-update + all-gather of one HPR iteration for the x-block [j0, j1) this GPU owns:
 //   wait until every rank's partial w_q = A_q^T y_q is complete;  w_j = sum_q w_q[j] (P2P loads, rank order: the result
 //   does not depend on who finishes first);  x-update (same arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY
 //   rank's x_hat buffer (P2P stores);  the last CTA tells every rank that this block of x_hat is in place.
-template <bool CHECK>
+// PP = number of ranks (compile time: all PP peer loads of an element pair are issued before the first use -- one NVLink
+// round trip per pair instead of PP) or 0 (any rank count, loads one after the other).  16-byte accesses; j0 is even.
+template <bool CHECK, int PP>
 __global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs pp, int P, int rank, unsigned long long epoch, unsigned *done,
                                                                       double *x, const double *c, const double *l, const double *u,
                                                                       const double *x0, double *x_bar, double *z_bar, double *x_tmp,
@@ -263,16 +270,48 @@ __global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs 
     const int k = *kx;
     const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
-    for (int j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += gridDim.x * blockDim.x) {
+    auto update = [&](int j, double w, double xi, double cj, double lj, double uj, double x0j, double &xn, double &xh) {
+        const double zt = fma(sigma, w - cj, xi);
+        const double xb = fmin(uj, fmax(lj, zt));
+        xh = 2.0 * xb - xi;
+        xn = fma(f2, xh, f1 * x0j);
+        if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
+    };
+    const int npairs = (j1 - j0) >> 1;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs; t += gridDim.x * blockDim.x) {
+        const int j = j0 + 2 * t;
+        double2 w = make_double2(0.0, 0.0);
+        if (PP > 0) {
+            double2 wv[PP > 0 ? PP : 1];
+#pragma unroll
+            for (int q = 0; q < PP; ++q) wv[q] = ld_peer2(pp.w[q] + j);
+#pragma unroll
+            for (int q = 0; q < PP; ++q) { w.x += wv[q].x; w.y += wv[q].y; }
+        } else {
+            for (int q = 0; q < P; ++q) { const double2 v = ld_peer2(pp.w[q] + j); w.x += v.x; w.y += v.y; }
+        }
+        const double2 xi = *reinterpret_cast<const double2 *>(x + j), cj = *reinterpret_cast<const double2 *>(c + j);
+        const double2 lj = *reinterpret_cast<const double2 *>(l + j), uj = *reinterpret_cast<const double2 *>(u + j);
+        const double2 xa = *reinterpret_cast<const double2 *>(x0 + j);
+        double2 xn, xh;
+        update(j, w.x, xi.x, cj.x, lj.x, uj.x, xa.x, xn.x, xh.x);
+        update(j + 1, w.y, xi.y, cj.y, lj.y, uj.y, xa.y, xn.y, xh.y);
+        *reinterpret_cast<double2 *>(x + j) = xn;
+        if (PP > 0) {
+#pragma unroll
+            for (int q = 0; q < PP; ++q) *reinterpret_cast<double2 *>(pp.xhat[q] + j) = xh;
+        } else {
+            for (int q = 0; q < P; ++q) *reinterpret_cast<double2 *>(pp.xhat[q] + j) = xh;
+        }
+    }
+    if (((j1 - j0) & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd block length: the last entry
+        const int j = j1 - 1;
         double w = 0.0;
         for (int q = 0; q < P; ++q) w += ld_peer(pp.w[q] + j);
-        const double xi = x[j];
-        const double zt = fma(sigma, w - c[j], xi);
-        const double xb = fmin(u[j], fmax(l[j], zt));
-        const double xh = 2.0 * xb - xi;
-        x[j] = fma(f2, xh, f1 * x0[j]);
+        double xn, xh;
+        update(j, w, x[j], c[j], l[j], u[j], x0[j], xn, xh);
+        x[j] = xn;
         for (int q = 0; q < P; ++q) pp.xhat[q][j] = xh;
-        if (CHECK) { x_bar[j] = xb; z_bar[j] = (xb - zt) / sigma; x_tmp[j] = xb - xh; }
     }
     __threadfence_system();   // this thread's peer stores are performed before the CTA is counted as done
     __syncthreads();
@@ -462,7 +501,7 @@ static cudaMemPool_t engine_pool(int device) {
         props.location.type = cudaMemLocationTypeDevice;
         props.location.id = device;
         HPR_CUDA_CHECK(cudaMemPoolCreate(&g_pools[device], &props));
-        unsigned long long keep = 4096ULL << 20;
+        unsigned long long keep = 8192ULL << 20;
         if (const char *e = getenv("HPRLP_POOL_RETAIN_MB")) keep = strtoull(e, nullptr, 10) << 20;
         HPR_CUDA_CHECK(cudaMemPoolSetAttribute(g_pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
     }
@@ -653,7 +692,7 @@ constexpr size_t kUpChunk = (size_t)8 << 20;
 std::mutex g_stage_mu;
 char *g_stage[kUpThreads][2] = {};
 }
-static void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     static const bool off = getenv("HPRLP_PLAIN_H2D") != nullptr;
     if (off || bytes < ((size_t)32 << 20) || !g_stage_mu.try_lock()) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
@@ -700,6 +739,81 @@ static void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t str
     for (auto &w : workers) w.join();
     cudaEventDestroy(ready);
     for (cudaError_t e : errs) HPR_CUDA_CHECK(e);
+}
+
+// Device -> host copy of a large array into PAGEABLE (typically freshly malloc'ed) memory: the mirror image of h2d_large.
+// The worker threads also take the first-touch page faults of the destination in parallel.
+void d2h_large(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    static const bool off = getenv("HPRLP_PLAIN_H2D") != nullptr;
+    if (off || bytes < ((size_t)32 << 20) || !g_stage_mu.try_lock()) {
+        HPR_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_stage_mu, std::adopt_lock);
+    for (int t = 0; t < kUpThreads; ++t)
+        for (int b = 0; b < 2; ++b)
+            if (!g_stage[t][b]) HPR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&g_stage[t][b]), kUpChunk, cudaHostAllocPortable));
+    cudaEvent_t ready;   // the kernels that produce src are queued on the engine stream
+    HPR_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    HPR_CUDA_CHECK(cudaEventRecord(ready, stream));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::vector<std::thread> workers;
+    std::vector<cudaError_t> errs(kUpThreads, cudaSuccess);
+    for (int t = 0; t < kUpThreads; ++t) {
+        workers.emplace_back([&, t]() {
+            cudaSetDevice(dev);
+            const size_t lo = (bytes * t / kUpThreads) & ~(size_t)255, hi = (t + 1 == kUpThreads) ? bytes : ((bytes * (t + 1) / kUpThreads) & ~(size_t)255);
+            cudaStream_t st;
+            cudaEvent_t ev[2];
+            if ((errs[t] = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return;
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+            cudaStreamWaitEvent(st, ready, 0);
+            size_t pend_o[2] = {0, 0}, pend_len[2] = {0, 0};
+            int b = 0;
+            auto drain = [&](int bb) {   // chunk in staging buffer bb has arrived: hand it to the caller's array
+                if (!pend_len[bb]) return;
+                cudaEventSynchronize(ev[bb]);
+                std::memcpy(static_cast<char *>(dst) + pend_o[bb], g_stage[t][bb], pend_len[bb]);
+                pend_len[bb] = 0;
+            };
+            for (size_t o = lo; o < hi; o += kUpChunk, b ^= 1) {
+                const size_t len = std::min(kUpChunk, hi - o);
+                drain(b);
+                const cudaError_t e = cudaMemcpyAsync(g_stage[t][b], static_cast<const char *>(src) + o, len, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) { errs[t] = e; break; }
+                cudaEventRecord(ev[b], st);
+                pend_o[b] = o; pend_len[b] = len;
+            }
+            drain(b); drain(b ^ 1);
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (errs[t] == cudaSuccess) errs[t] = e;
+            cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+            cudaStreamDestroy(st);
+        });
+    }
+    for (auto &w : workers) w.join();
+    cudaEventDestroy(ready);
+    for (cudaError_t e : errs) HPR_CUDA_CHECK(e);
+}
+
+// One zero-filled block from the engines' private pool (batched solver state), stream-ordered.
+void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st) {
+    void *p = nullptr;
+    static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
+    if (no_pool) HPR_CUDA_CHECK(cudaMalloc(&p, bytes));
+    else HPR_CUDA_CHECK(cudaMallocFromPoolAsync(&p, bytes, engine_pool(device), st));
+    HPR_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+    return p;
+}
+void pool_free(void *p, cudaStream_t st) {
+    if (!p) return;
+    static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
+    if (no_pool) { cudaFree(p); return; }
+    cudaFreeAsync(p, st);
+    cudaStreamSynchronize(st);
 }
 
 void Engine::upload(const LP_info_cpu *lp, int dev) {
@@ -755,7 +869,7 @@ void Engine::prepare(int m_, int n_, long long nnz_, int dev) {
         // Stream-ordered allocation from a PRIVATE memory pool per device (the process's default pool is left alone): the
         // arena of a finished solve stays cached up to the pool's release threshold, so repeated solve() calls pay neither
         // cudaMalloc nor cudaFree (both synchronous and ~0.1-0.5 s for multi-GB buffers).  HPRLP_POOL_RETAIN_MB bounds what
-        // stays cached (default 4096 MB; 0 = return everything as soon as an engine is destroyed);
+        // stays cached (default 8192 MB; 0 = return everything as soon as an engine is destroyed);
         // hprlp_b200_release_cached_memory() returns it all on demand.  HPRLP_NO_POOL=1 restores cudaMalloc/cudaFree.
         static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
         pooled_ = !no_pool;
@@ -1065,8 +1179,22 @@ void Engine::exchange_x(bool check) {
         for (int q = 0; q < kMaxPeers; ++q) { pp.w[q] = px->w[q]; pp.xhat[q] = px->xhat[q]; pp.flags[q] = px->flags[q]; }
         const unsigned long long e = ++px->epoch;
         exchange_signal_kernel<<<1, 32, 0, stream>>>(pp, nranks, rank, 0, e);
-        if (check) fused_exchange_x_kernel<true><<<gx, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, x_bar, z_bar, x_tmp, d_params, d_k, d_k + 1, xb0, xb1);
-        else fused_exchange_x_kernel<false><<<gx, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+        const int gp = vec_grid((xb1 - xb0 + 1) / 2);   // one element pair per thread and pass
+        auto launch = [&](auto kernel, bool chk) {
+            kernel<<<gp, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr, chk ? z_bar : nullptr,
+                                                   chk ? x_tmp : nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+        };
+        if (check) launch(fused_exchange_x_kernel<true, 0>, true);   // check iterations are rare: one generic instantiation
+        else switch (nranks) {
+            case 2: launch(fused_exchange_x_kernel<false, 2>, false); break;
+            case 3: launch(fused_exchange_x_kernel<false, 3>, false); break;
+            case 4: launch(fused_exchange_x_kernel<false, 4>, false); break;
+            case 5: launch(fused_exchange_x_kernel<false, 5>, false); break;
+            case 6: launch(fused_exchange_x_kernel<false, 6>, false); break;
+            case 7: launch(fused_exchange_x_kernel<false, 7>, false); break;
+            case 8: launch(fused_exchange_x_kernel<false, 8>, false); break;
+            default: launch(fused_exchange_x_kernel<false, 0>, false); break;
+        }
         exchange_wait_kernel<<<1, 32, 0, stream>>>(px->flags[rank], nranks, 1, e);
         launches += 3;
         return;

@@ -221,8 +221,12 @@ struct hprlp_b200_comm {
 namespace hpr {
 void fill_b200_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info);
 
-// device memory pool of the engines (engine.cu)
+// device memory pool of the engines, staged copies of large pageable arrays (engine.cu)
 void release_cached_device_memory();
+void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st);
+void pool_free(void *p, cudaStream_t st);
+void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // src may be reused on return; dst is stream-ordered
+void d2h_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // returns when the copy is complete
 
 // presolve bridge (presolve.cpp); returns false when unavailable / failed (caller solves the original model)
 bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_info_cpu *reduced, void **handle);

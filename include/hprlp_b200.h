@@ -126,7 +126,7 @@ int hprlp_b200_presolve(const LP_info_cpu *model, const HPRLP_parameters *param,
 void hprlp_b200_presolve_free(void *handle, LP_info_cpu *reduced);
 
 /* Finished solves keep their device arena cached in a private stream-ordered memory pool (per device, bounded by
- * HPRLP_POOL_RETAIN_MB, default 4096) so that repeated solve() calls skip cudaMalloc/cudaFree.  This call returns all
+ * HPRLP_POOL_RETAIN_MB, default 8192) so that repeated solve() calls skip cudaMalloc/cudaFree.  This call returns all
  * cached memory to the driver (cudaMemPoolTrimTo 0).  The reference frees everything at the end of each solve. */
 void hprlp_b200_release_cached_memory(void);
 
