@@ -74,35 +74,40 @@ __device__ __forceinline__ void st_once(double *p, double v) { __stcs(p, v); }
 // ---------------------------------------------------------------------------------------------
 // skeleton: one warp per row, lane = instance of group blockIdx.y
 // ---------------------------------------------------------------------------------------------
+// Register blocking over the batch: one pass over the matrix serves Op::kNG groups of 32 instances (lane = instance
+// inside each group), so every (col, val) pair -- loaded once per 32 nonzeros and broadcast by two shuffles -- feeds kNG
+// independent gathers + FMAs per lane.  r1 ran one group per pass and was issue / L1-bound (ncu: IPC 2.2, L1TEX 65 %,
+// DRAM 50 %): per nonzero it spent 3 SHFL + address arithmetic + loop control on ONE useful FMA per lane.
 template <class Op>
-__global__ void __launch_bounds__(kBThreads) batched_rows_kernel(BView M, Op op) {
-    constexpr int NV = Op::NV;
+__global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 4 : 6)) batched_rows_kernel(BView M, Op op, int G) {
+    constexpr int NG = Op::kNG;
     __shared__ double red[kBWarps][kMaxSlots][kGS];
-    const int g = blockIdx.y;
+    const int g0 = blockIdx.y * NG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    op.init(g, lane);
+    op.init(g0, lane, G);
     const unsigned long long keep = make_keep_policy();
     const int row0 = blockIdx.x * kRowsPerCta;
     const int row1 = min(M.rows, row0 + kRowsPerCta);
-    const size_t gbase = (size_t)g * M.gcols;
     for (int r = row0 + warp; r < row1; r += kBWarps) {
         const int p0 = M.rowPtr[r], p1 = M.rowPtr[r + 1];
-        double acc[NV];
+        double acc[NG];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+        for (int q = 0; q < NG; ++q) acc[q] = 0.0;
         for (int k0 = p0; k0 < p1; k0 += 32) {
             const int kk = k0 + lane;
             const int c = (kk < p1) ? __ldg(M.col + kk) : 0;
             const double v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
             const int cnt = min(32, p1 - k0);
-#pragma unroll 8
+#pragma unroll 4
             for (int t = 0; t < cnt; ++t) {
                 const int cc = __shfl_sync(0xffffffffu, c, t);
                 const double vv = __shfl_sync(0xffffffffu, v, t);
-                op.accum(vv, (gbase + cc) * kGS + lane, acc, keep);
+#pragma unroll
+                for (int q = 0; q < NG; ++q) op.accum(vv, cc, q, acc[q], keep);
             }
         }
-        op.row(r, ((size_t)g * M.rows + r) * kGS + lane, acc);
+#pragma unroll
+        for (int q = 0; q < NG; ++q) op.row(r, q, acc[q]);
     }
     op.finish(red, warp, lane);
 }
@@ -134,14 +139,35 @@ __global__ void batched_final_reduce_kernel(const double *partials, int nbx, int
     out[(size_t)s * Bpad + g * kGS + lane] = v;
 }
 
+// Per-thread state shared by every op: where the gathered operand and the row-indexed arrays of each of the NG groups
+// start for this lane.  Groups beyond G (last pass of a batch whose group count is not a multiple of NG) alias group g0
+// for the gathers and are switched off for the epilogue.
+template <int NG>
 struct BOpBase {
-    static constexpr int NV = 1;
+    static constexpr int kNG = NG;
+    int gcols, orows;               // rows of the gathered operand / of the output-side arrays
+    const double *gp[NG];           // gathered operand of group q at row 0, this lane
+    size_t obase[NG];               // offset of (group q, row 0, this lane) in the row-indexed arrays
+    bool valid[NG];
+    __device__ __forceinline__ void init_base(const double *gathered, int g0, int lane, int G) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            valid[q] = g0 + q < G;
+            const int g = valid[q] ? g0 + q : g0;
+            gp[q] = gathered + (size_t)g * gcols * kGS + lane;
+            obase[q] = (size_t)g * orows * kGS + lane;
+        }
+    }
+    __device__ __forceinline__ void accum(double v, int col, int q, double &acc, unsigned long long keep) const {
+        acc = fma(v, ld_keep(gp[q] + (size_t)col * kGS, keep), acc);
+    }
     __device__ __forceinline__ void finish(double (*)[kMaxSlots][kGS], int, int) {}
 };
 
 // x-phase (reference update_x_z_{normal,check}_batched_kernel, src/batched_solver.cu:122-178)
-template <bool CHECK>
-struct BXOp : BOpBase {
+template <bool CHECK, int NG>
+struct BXOp : BOpBase<NG> {
+    using Base = BOpBase<NG>;
     const double *Y;
     double *X, *X_hat;
     const double *L, *U, *C, *lastX;
@@ -150,38 +176,43 @@ struct BXOp : BOpBase {
     const int *kx;
     int *ky;
     const unsigned char *active;
-    double sig, f1, f2;
-    bool on;
-    __device__ __forceinline__ void init(int g, int lane) {
-        const int inst = g * kGS + lane;
-        sig = sigma[inst];
-        on = active[inst] != 0;
-        const int k = kx[inst];
-        f1 = 1.0 / (k + 2.0);
-        f2 = 1.0 - f1;
-        if (blockIdx.x == 0 && threadIdx.x < 32) ky[inst] = k;
+    double sig[NG], f1[NG], f2[NG];
+    bool on[NG];
+    __device__ __forceinline__ void init(int g0, int lane, int G) {
+        Base::init_base(Y, g0, lane, G);
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const int inst = (Base::valid[q] ? g0 + q : g0) * kGS + lane;
+            sig[q] = sigma[inst];
+            on[q] = Base::valid[q] && active[inst] != 0;
+            const int k = kx[inst];
+            f1[q] = 1.0 / (k + 2.0);
+            f2[q] = 1.0 - f1[q];
+            if (Base::valid[q] && blockIdx.x == 0 && threadIdx.x < 32) ky[inst] = k;
+        }
     }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(Y + gi, keep), acc[0]); }
-    __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
-        if (!on) return;
+    __device__ __forceinline__ void row(int r, int q, double acc) const {
+        if (!on[q]) return;
+        const size_t t = Base::obase[q] + (size_t)r * kGS;
         const double xi = ld_once(X + t);
-        const double zt = fma(sig, acc[0] - ld_once(C + t), xi);
+        const double zt = fma(sig[q], acc - ld_once(C + t), xi);
         const double xb = fmin(fmax(zt, ld_once(L + t)), ld_once(U + t));
         const double xh = 2.0 * xb - xi;
         if (CHECK) {
             st_once(DX + t, xb - xh);
-            st_once(Z_bar + t, (xb - zt) / sig);
+            st_once(Z_bar + t, (xb - zt) / sig[q]);
             st_once(X_bar + t, xb);
         }
         X_hat[t] = xh;   // gathered by the y-phase that follows: normal priority
-        st_once(X + t, fma(f2, xh, f1 * ld_once(lastX + t)));
+        st_once(X + t, fma(f2[q], xh, f1[q] * ld_once(lastX + t)));
     }
 };
 
 // y-phase (reference update_y_{normal,check}_batched_kernel :180-236): y_bar = d / (lambda sigma) (a division
 // here, a reciprocal multiply in the single-instance path -- reference quirk #5)
-template <bool CHECK>
-struct BYOp : BOpBase {
+template <bool CHECK, int NG>
+struct BYOp : BOpBase<NG> {
+    using Base = BOpBase<NG>;
     const double *X_hat;
     double *Y;
     const double *AL, *AU, *lastY;
@@ -191,46 +222,50 @@ struct BYOp : BOpBase {
     int *kx;
     const unsigned char *active;
     double lambda_max;
-    double fact1, f1, f2;
-    bool on;
-    __device__ __forceinline__ void init(int g, int lane) {
-        const int inst = g * kGS + lane;
-        fact1 = lambda_max * sigma[inst];
-        on = active[inst] != 0;
-        const int k = ky[inst];
-        f1 = 1.0 / (k + 2.0);
-        f2 = 1.0 - f1;
-        if (blockIdx.x == 0 && threadIdx.x < 32 && on) kx[inst] = k + 1;
+    double fact1[NG], f1[NG], f2[NG];
+    bool on[NG];
+    __device__ __forceinline__ void init(int g0, int lane, int G) {
+        Base::init_base(X_hat, g0, lane, G);
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const int inst = (Base::valid[q] ? g0 + q : g0) * kGS + lane;
+            fact1[q] = lambda_max * sigma[inst];
+            on[q] = Base::valid[q] && active[inst] != 0;
+            const int k = ky[inst];
+            f1[q] = 1.0 / (k + 2.0);
+            f2[q] = 1.0 - f1[q];
+            if (on[q] && blockIdx.x == 0 && threadIdx.x < 32) kx[inst] = k + 1;
+        }
     }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(X_hat + gi, keep), acc[0]); }
-    __device__ __forceinline__ void row(int, size_t t, const double (&acc)[1]) const {
-        if (!on) return;
+    __device__ __forceinline__ void row(int r, int q, double acc) const {
+        if (!on[q]) return;
+        const size_t t = Base::obase[q] + (size_t)r * kGS;
         const double yi = ld_once(Y + t);
-        const double v = fma(-fact1, yi, acc[0]);
+        const double v = fma(-fact1[q], yi, acc);
         const double d = fmax(ld_once(AL + t) - v, fmin(ld_once(AU + t) - v, 0.0));
-        const double yb = d / fact1;
+        const double yb = d / fact1[q];
         const double yh = 2.0 * yb - yi;
         if (CHECK) {
             st_once(DY + t, yb - yh);
             st_once(Y_bar + t, yb);
             st_once(Y_obj + t, v + d);
         }
-        Y[t] = fma(f2, yh, f1 * ld_once(lastY + t));   // gathered by the next x-phase: normal priority
+        Y[t] = fma(f2[q], yh, f1[q] * ld_once(lastY + t));   // gathered by the next x-phase: normal priority
     }
 };
 
 // dual residual + objective terms (reference compute_batched_Rd_kernel :238-249 + cublasDdot/Dnrm2 :604-607,
 // lu violation :265-278,615-617): slots 0 |RD|^2, 1 <C,X_bar>, 2 <X_bar,Z_bar>, 3 |lu/col_norm|^2 (iter 0)
 template <bool ITER0>
-struct BResDualOp : BOpBase {
+struct BResDualOp : BOpBase<1> {
     const double *Y_bar, *C, *Z_bar, *X_bar, *L, *U, *col_norm;
     double *partials;
     double t[4];
-    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = t[2] = t[3] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(Y_bar + gi, keep), acc[0]); }
-    __device__ __forceinline__ void row(int j, size_t i, const double (&acc)[1]) {
+    __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(Y_bar, g0, lane, G); t[0] = t[1] = t[2] = t[3] = 0.0; }
+    __device__ __forceinline__ void row(int j, int, double acc) {
+        const size_t i = obase[0] + (size_t)j * kGS;
         const double cj = C[i], zb = Z_bar[i], xb = X_bar[i], cn = col_norm[j];
-        const double rd = (cj - acc[0] - zb) * cn;
+        const double rd = (cj - acc - zb) * cn;
         t[0] += rd * rd;
         t[1] += cj * xb;
         t[2] += xb * zb;
@@ -247,14 +282,13 @@ struct BResDualOp : BOpBase {
 };
 
 // primal residual (reference compute_batched_Rp_kernel :251-263 + :605,608): slots 0 |RP|^2, 1 <Y_obj,Y_bar>
-struct BResPrimalOp : BOpBase {
+struct BResPrimalOp : BOpBase<1> {
     const double *X_bar, *AL, *AU, *row_norm, *Y_obj, *Y_bar;
     double *partials;
     double t[2];
-    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(X_bar + gi, keep), acc[0]); }
-    __device__ __forceinline__ void row(int r, size_t i, const double (&acc)[1]) {
-        const double ax = acc[0];
+    __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(X_bar, g0, lane, G); t[0] = t[1] = 0.0; }
+    __device__ __forceinline__ void row(int r, int, double ax) {
+        const size_t i = obase[0] + (size_t)r * kGS;
         const double rp = row_norm[r] * fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax);
         t[0] += rp * rp;
         t[1] += Y_obj[i] * Y_bar[i];
@@ -265,15 +299,14 @@ struct BResPrimalOp : BOpBase {
 };
 
 // M-norm terms (reference compute_weighted_norm :625-650): slots 0 <A DX, DY>, 1 |DY|^2
-struct BWeightedOp : BOpBase {
+struct BWeightedOp : BOpBase<1> {
     const double *DX, *DY;
     double *partials;
     double t[2];
-    __device__ __forceinline__ void init(int, int) { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void accum(double v, size_t gi, double (&acc)[1], unsigned long long keep) const { acc[0] = fma(v, ld_keep(DX + gi, keep), acc[0]); }
-    __device__ __forceinline__ void row(int, size_t i, const double (&acc)[1]) {
-        const double dy = DY[i];
-        t[0] += acc[0] * dy;
+    __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(DX, g0, lane, G); t[0] = t[1] = 0.0; }
+    __device__ __forceinline__ void row(int r, int, double acc) {
+        const double dy = DY[obase[0] + (size_t)r * kGS];
+        t[0] += acc * dy;
         t[1] += dy * dy;
     }
     __device__ __forceinline__ void finish(double (*red)[kMaxSlots][kGS], int warp, int lane) {
@@ -567,8 +600,9 @@ class BatchedSolver {
 
     BView viewA() const { return BView{m, n, eng.A.rowPtr, eng.A.col, eng.A.val}; }
     BView viewAT() const { return BView{n, m, eng.AT.rowPtr, eng.AT.col, eng.AT.val}; }
-    dim3 gridA() const { return dim3(nbx_A, G); }
-    dim3 gridAT() const { return dim3(nbx_AT, G); }
+    dim3 gridA(int ng = 1) const { return dim3(nbx_A, (G + ng - 1) / ng); }
+    dim3 gridAT(int ng = 1) const { return dim3(nbx_AT, (G + ng - 1) / ng); }
+    int ngx = 4, ngy = 2;   // groups of 32 instances per pass of the x- / y-phase (HPRLP_BATCH_NGX / _NGY: 1, 2 or 4)
 
     void fetch(int slots) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * (size_t)slots * Bpad, cudaMemcpyDeviceToHost, stream));
@@ -576,30 +610,35 @@ class BatchedSolver {
     }
     double hs(int slot, int k) const { return h_scal[(size_t)slot * Bpad + k]; }
 
+    template <bool CHECK, int NG>
+    void launch_x() {
+        BXOp<CHECK, NG> ox{};
+        ox.gcols = m; ox.orows = n;
+        ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
+        ox.DX = DX; ox.Z_bar = Z_bar; ox.X_bar = X_bar; ox.sigma = d_sigma; ox.kx = d_k; ox.ky = d_k + Bpad; ox.active = d_active;
+        batched_rows_kernel<<<gridAT(NG), kBThreads, 0, stream>>>(viewAT(), ox, G);
+    }
+    template <bool CHECK, int NG>
+    void launch_y() {
+        BYOp<CHECK, NG> oy{};
+        oy.gcols = n; oy.orows = m;
+        oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY; oy.DY = DY; oy.Y_bar = Y_bar; oy.Y_obj = Y_obj;
+        oy.sigma = d_sigma; oy.ky = d_k + Bpad; oy.kx = d_k; oy.active = d_active; oy.lambda_max = lambda_max;
+        batched_rows_kernel<<<gridA(NG), kBThreads, 0, stream>>>(viewA(), oy, G);
+    }
     void iteration(bool check) {
-        const int *kx = d_k; int *kxw = d_k; int *ky = d_k + Bpad;
-        if (check) {
-            BXOp<true> ox{}; ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
-            ox.DX = DX; ox.Z_bar = Z_bar; ox.X_bar = X_bar; ox.sigma = d_sigma; ox.kx = kx; ox.ky = ky; ox.active = d_active;
-            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), ox);
-            BYOp<true> oy{}; oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY; oy.DY = DY; oy.Y_bar = Y_bar;
-            oy.Y_obj = Y_obj; oy.sigma = d_sigma; oy.ky = ky; oy.kx = kxw; oy.active = d_active; oy.lambda_max = lambda_max;
-            batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), oy);
-        } else {
-            BXOp<false> ox{}; ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
-            ox.sigma = d_sigma; ox.kx = kx; ox.ky = ky; ox.active = d_active;
-            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), ox);
-            BYOp<false> oy{}; oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY;
-            oy.sigma = d_sigma; oy.ky = ky; oy.kx = kxw; oy.active = d_active; oy.lambda_max = lambda_max;
-            batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), oy);
+        if (check) { launch_x<true, 1>(); launch_y<true, 1>(); }   // 1 in 10 iterations at most: one instantiation each
+        else {
+            if (ngx >= 4) launch_x<false, 4>(); else if (ngx == 2) launch_x<false, 2>(); else launch_x<false, 1>();
+            if (ngy >= 4) launch_y<false, 4>(); else if (ngy == 2) launch_y<false, 2>(); else launch_y<false, 1>();
         }
         launches += 2;
     }
 
     // reference compute_weighted_norm :625-650 (lambda_max shared by the batch, only ever increased)
     std::vector<double> weighted_norm(const std::vector<double> &sigma) {
-        BWeightedOp o{}; o.DX = DX; o.DY = DY; o.partials = d_partials;
-        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), o);
+        BWeightedOp o{}; o.gcols = n; o.orows = m; o.DX = DX; o.DY = DY; o.partials = d_partials;
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), o, G);
         batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal);
         batched_sumsq_kernel<<<dim3(nbx_vec, G), kBThreads, 0, stream>>>(DX, n, d_partials);
         batched_final_reduce_kernel<<<G, 32, 0, stream>>>(d_partials, nbx_vec, 1, Bpad, d_scal + 2 * (size_t)Bpad);
@@ -622,18 +661,18 @@ class BatchedSolver {
     // reference compute_residuals :578-623
     void residuals(int iter, ResidualHost *res) {
         if (iter == 0) {
-            BResDualOp<true> o{}; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
+            BResDualOp<true> o{}; o.gcols = m; o.orows = n; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
             o.col_norm = eng.col_norm; o.partials = d_partials;
-            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o);
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o, G);
         } else {
-            BResDualOp<false> o{}; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
+            BResDualOp<false> o{}; o.gcols = m; o.orows = n; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
             o.col_norm = eng.col_norm; o.partials = d_partials;
-            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o);
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o, G);
         }
         batched_final_reduce_kernel<<<G, 32 * 4, 0, stream>>>(d_partials, nbx_AT, 4, Bpad, d_scal);
-        BResPrimalOp p{}; p.X_bar = X_bar; p.AL = AL; p.AU = AU; p.row_norm = eng.row_norm; p.Y_obj = Y_obj; p.Y_bar = Y_bar;
+        BResPrimalOp p{}; p.gcols = n; p.orows = m; p.X_bar = X_bar; p.AL = AL; p.AU = AU; p.row_norm = eng.row_norm; p.Y_obj = Y_obj; p.Y_bar = Y_bar;
         p.partials = d_partials;
-        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), p);
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), p, G);
         batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal + 4 * (size_t)Bpad);
         launches += 4;
         fetch(6);
@@ -706,10 +745,12 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         S.eng.scale(&mp);
     }
     S.stream = S.eng.stream;
+    if (const char *e = getenv("HPRLP_BATCH_NGX")) S.ngx = atoi(e);
+    if (const char *e = getenv("HPRLP_BATCH_NGY")) S.ngy = atoi(e);
     cudaStream_t st = S.stream;
     const bool bc = actual.use_bc_scaling;
     static const bool timing = getenv("HPRLP_TIMING") != nullptr;   // stage wall times on stderr
-    double t_mark = now_s();
+    double t_mark = setup_start;
     auto stage_done = [&](const char *what) {
         if (!timing) return;
         cudaStreamSynchronize(st);
