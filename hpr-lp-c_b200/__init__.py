@@ -95,7 +95,7 @@ EXTENDED_SYMBOLS = ["hprlp_b200_solve_ex", "hprlp_b200_power_start", "hprlp_b200
                     "hprlp_b200_solve_batched_multi", "hprlp_b200_solve_partitioned", "hprlp_b200_presolve", "hprlp_b200_presolve_free", "hprlp_b200_solve_partitioned_synth", "hprlp_b200_synth_rows", "hprlp_b200_profiler_start", "hprlp_b200_profiler_stop", "hprlp_b200_version",
                     "hprlp_b200_solve_partitioned_local", "hprlp_b200_nccl_unique_id", "hprlp_b200_solve_partitioned_rank",
                     "hprlp_b200_engine_create_rank", "hprlp_b200_nccl_exchange_ms", "hprlp_b200_solve_partitioned_synth_rank",
-                    "hprlp_b200_comm_create", "hprlp_b200_comm_destroy",
+                    "hprlp_b200_comm_create", "hprlp_b200_comm_destroy", "hprlp_b200_warmup", "hprlp_b200_solve_batched_layout",
                     "hprlp_b200_release_cached_memory"]
 
 
@@ -173,6 +173,8 @@ class HprLib:
             L.hprlp_b200_solve_partitioned.argtypes = [C.POINTER(LPInfoCpu), C.POINTER(Parameters), C.c_int, C.c_int, C.POINTER(B200Info)]
             L.hprlp_b200_solve_batched_multi.restype = BatchedResults
             L.hprlp_b200_solve_batched_multi.argtypes = L.solve_batched.argtypes + [C.c_int]
+            L.hprlp_b200_solve_batched_layout.restype = BatchedResults
+            L.hprlp_b200_solve_batched_layout.argtypes = L.solve_batched.argtypes + [C.c_int]
             L.hprlp_b200_solve_partitioned_local.restype = Results
             L.hprlp_b200_solve_partitioned_local.argtypes = L.hprlp_b200_solve_partitioned.argtypes
             L.hprlp_b200_nccl_unique_id.restype = C.c_int
@@ -354,15 +356,35 @@ class HprLib:
             raise RuntimeError("hprlp_b200_scale_only failed")
         return o
 
-    def solve_batched(self, model, C_, AL, AU, l, u, obj_constants=None, param=None, n_gpus=None):
+    def solve_batched_nB(self, model, C_, AL, AU, l, u, obj_constants=None, param=None):
+        """The reference's Python calling convention: C, l, u of shape (n, B) and AL, AU of shape (m, B), any memory order.
+        C-ordered arrays (numpy's default) go through hprlp_b200_solve_batched_layout(layout=1) without any host copy;
+        Fortran-ordered ones are already the ABI's column-major layout.  Returns x, z as (n, B) and y as (m, B) views."""
+        arrs = [np.asarray(a, dtype=np.float64) for a in (C_, AL, AU, l, u)]
+        B = arrs[0].shape[1]
+        if all(a.flags.c_contiguous for a in arrs):
+            layout = 1
+        else:
+            arrs = [np.asfortranarray(a) for a in arrs]
+            layout = 0
+        out = self.solve_batched(model, *[a if layout == 1 else a.T for a in arrs], obj_constants, param, _layout=layout, _B=B)
+        for k in ("x", "y", "z"):
+            if k in out:
+                out[k] = out[k].T
+        return out
+
+    def solve_batched(self, model, C_, AL, AU, l, u, obj_constants=None, param=None, n_gpus=None, _layout=None, _B=None):
         """Dense inputs column-major: arrays of shape (B, n) / (B, m) in C order == n x B column-major."""
         mm = model.contents
         m, n = mm.m, mm.n
         C_, AL, AU, l, u = (_f64(a) for a in (C_, AL, AU, l, u))
-        B = C_.shape[0]
+        B = C_.shape[0] if _B is None else _B
         oc = _f64(obj_constants) if obj_constants is not None else None
         args = (model, B, _dp(C_), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(oc), C.byref(param) if param is not None else None)
-        res = self.lib.solve_batched(*args) if n_gpus is None else self.lib.hprlp_b200_solve_batched_multi(*args, int(n_gpus))
+        if _layout is not None:
+            res = self.lib.hprlp_b200_solve_batched_layout(*args, int(_layout))
+        else:
+            res = self.lib.solve_batched(*args) if n_gpus is None else self.lib.hprlp_b200_solve_batched_multi(*args, int(n_gpus))
         out = dict(m=res.m, n=res.n, batch_size=res.batch_size, time=res.time, setup_time=res.setup_time,
                    solve_time=res.solve_time, power_time=res.power_time)
         if res.status:

@@ -7,7 +7,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <atomic>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/HPRLP.h"
@@ -68,6 +71,32 @@ void fill_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *info) { 
 
 }  // namespace
 
+// ---- first-solve warm-up: one background thread per device, started at most once per process ------------------------
+namespace {
+std::mutex g_warm_mu;
+std::thread g_warm_thread[64];
+bool g_warm_started[64] = {};
+void warm_start(int device) {
+    if (device < 0 || device >= 64 || getenv("HPRLP_NO_WARMUP")) return;
+    std::lock_guard<std::mutex> lk(g_warm_mu);
+    if (g_warm_started[device]) return;
+    g_warm_started[device] = true;
+    g_warm_thread[device] = std::thread([device] { hpr::warm_device(device); });
+}
+void warm_wait(int device) {
+    if (device < 0 || device >= 64) return;
+    std::thread t;
+    {
+        std::lock_guard<std::mutex> lk(g_warm_mu);
+        if (g_warm_thread[device].joinable()) t = std::move(g_warm_thread[device]);
+    }
+    if (t.joinable()) t.join();
+}
+struct WarmJoiner {   // no joinable std::thread may be left at process exit
+    ~WarmJoiner() { for (int d = 0; d < 64; ++d) warm_wait(d); }
+} g_warm_joiner;
+}  // namespace
+
 struct hprlp_b200_engine {
     Engine eng;
     HPRLP_parameters param;
@@ -103,6 +132,7 @@ static HPRLP_results solve_ex_impl(const LP_info_cpu *lp, const HPRLP_parameters
     }
     HPRLP_parameters def;
     const HPRLP_parameters *param = param_in ? param_in : &def;
+    warm_wait(param->device_number);   // a warm-up started earlier (hprlp_b200_warmup / solve with presolve) must be through
     if (!quiet) print_banner_and_params(param);
     static const bool timing = getenv("HPRLP_TIMING") != nullptr;   // stage wall times (with device syncs) on stderr
     const double t0 = now_seconds();
@@ -266,6 +296,10 @@ int hprlp_b200_scale_only(const LP_info_cpu *lp, const HPRLP_parameters *param_i
     });
 }
 
+// Starts the first-solve warm-up (CUDA context, module load, cuRAND) of `device` on a background thread and returns at
+// once; the next solve on that device waits for it.  build/solve_mps_file calls it before parsing the MPS file.
+void hprlp_b200_warmup(int device) { warm_start(device); }
+
 void hprlp_b200_profiler_start(void) { cudaProfilerStart(); }
 void hprlp_b200_profiler_stop(void) { cudaProfilerStop(); }
 
@@ -354,6 +388,10 @@ HPRLP_results solve(const LP_info_cpu *model, const HPRLP_parameters *param) {
     const HPRLP_parameters *actual = param ? param : &default_param;
     if (!actual->use_presolve) return HPRLP_main_solve(model, actual);
     return hpr::abi_guard_results("solve", [&]() -> HPRLP_results {
+    // PSLP runs in this process (no fork), so the first solve of a process can create its CUDA context and load cuRAND
+    // on a second host thread WHILE the presolve runs on this one (the reference's forked worker cannot be overlapped
+    // with CUDA initialisation in the parent without risking a fork of a CUDA process).  No-op from the second solve on.
+    warm_start(actual->device_number);
     LP_info_cpu reduced{};
     void *handle = nullptr;
     const bool presolve_ok = hpr::presolve_run(model, actual, &reduced, &handle);

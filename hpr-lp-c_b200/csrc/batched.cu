@@ -74,10 +74,11 @@ __device__ __forceinline__ void st_once(double *p, double v) { __stcs(p, v); }
 // ---------------------------------------------------------------------------------------------
 // skeleton: one warp per row, lane = instance of group blockIdx.y
 // ---------------------------------------------------------------------------------------------
-// Register blocking over the batch: one pass over the matrix serves Op::kNG groups of 32 instances (lane = instance
+// Register blocking over the batch: one pass over the matrix can serve Op::kNG groups of 32 instances (lane = instance
 // inside each group), so every (col, val) pair -- loaded once per 32 nonzeros and broadcast by two shuffles -- feeds kNG
-// independent gathers + FMAs per lane.  r1 ran one group per pass and was issue / L1-bound (ncu: IPC 2.2, L1TEX 65 %,
-// DRAM 50 %): per nonzero it spent 3 SHFL + address arithmetic + loop control on ONE useful FMA per lane.
+// independent gathers + FMAs per lane and A is streamed once per kNG groups.  Built and measured in round 2: it does NOT
+// pay on B200 (see BatchedSolver::ngx) -- the passes are limited by the bytes the gathers pull through the L2, which
+// register blocking does not reduce, and kNG slabs thrash the L2 -- so kNG = 1 is the default.
 template <class Op>
 __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 4 : 6)) batched_rows_kernel(BView M, Op op, int G) {
     constexpr int NG = Op::kNG;
@@ -525,6 +526,23 @@ __global__ void to_group_layout_scaled_kernel(const double *src, double *dst, in
     }
 }
 
+// row-major (rows x B, numpy's default order for an (n, B) array) -> column-major staging (instance k, row i at k*rows + i):
+// what the reference's Python binding does element by element on the host (bindings/python/src/hprlp_pybind.cpp:343-356)
+__global__ void rowmajor_to_colmajor_kernel(const double *src, double *dst, int rows, int B) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, k = k0 + tx;
+        if (r < rows && k < B) tile[j][tx] = src[(size_t)r * B + k];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int k = k0 + j, r = r0 + tx;
+        if (r < rows && k < B) dst[(size_t)k * rows + r] = tile[tx][j];
+    }
+}
+
 // pinned host blocks recycled for the life of the process (cudaFreeHost synchronises the device: engine.cu)
 std::mutex g_bpin_mu;
 std::vector<std::pair<double *, size_t>> g_bpin_free;
@@ -592,6 +610,7 @@ class BatchedSolver {
     double *d_stage2 = nullptr;  // second / third column-major staging buffers (m * B each) for AL, AU
     double *d_stage3 = nullptr;
     double *d_norms = nullptr;   // [6][Bpad]: norm_b_org, b_scale, norm_c_org, c_scale, norm_b, norm_c
+    double *d_raw = nullptr;     // row-major inputs as uploaded (layout 1 only)
 
     ~BatchedSolver() {
         if (arena) pool_free(arena, stream);
@@ -602,7 +621,11 @@ class BatchedSolver {
     BView viewAT() const { return BView{n, m, eng.AT.rowPtr, eng.AT.col, eng.AT.val}; }
     dim3 gridA(int ng = 1) const { return dim3(nbx_A, (G + ng - 1) / ng); }
     dim3 gridAT(int ng = 1) const { return dim3(nbx_AT, (G + ng - 1) / ng); }
-    int ngx = 4, ngy = 2;   // groups of 32 instances per pass of the x- / y-phase (HPRLP_BATCH_NGX / _NGY: 1, 2 or 4)
+    // Groups of 32 instances per pass of the x- / y-phase (HPRLP_BATCH_NGX / _NGY: 1, 2 or 4).  Measured on configs[3]
+    // (B200, 300 iterations, profiles/r2_batched_group_sweep.md): (1,1) 421 ms, (2,1) 429, (4,1) 481, (2,2) 453, (4,2) 504,
+    // (4,4) 591 -- more groups per pass means more gathered slabs competing for the L2, and the passes are bound by L2
+    // throughput on the 256-byte gathers (ncu: ~9-10 TB/s through the L2 against ~4 TB/s from DRAM), not by issue.
+    int ngx = 1, ngy = 1;
 
     void fetch(int slots) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(h_scal, d_scal, sizeof(double) * (size_t)slots * Bpad, cudaMemcpyDeviceToHost, stream));
@@ -720,10 +743,11 @@ using namespace hpr;
 extern "C" void free_batched_results(HPRLP_batched_results *results);
 
 // One GPU: the whole batch on device param->device_number.
+// layout 0: inputs column-major (the ABI: instance k contiguous); 1: row-major rows x B (C-ordered numpy (n, B) arrays)
 static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
                                                      const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in, const HPRLP_FLOAT *l_in,
                                                      const HPRLP_FLOAT *u_in, const HPRLP_FLOAT *obj_constants,
-                                                     const HPRLP_parameters *param) {
+                                                     const HPRLP_parameters *param, int layout = 0) {
     HPRLP_parameters def;
     HPRLP_parameters actual = param ? *param : def;
     actual.use_presolve = false;
@@ -777,6 +801,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         const size_t o_part = take(nblk * kMaxSlots * kGS * 8), o_scal = take((size_t)kMaxSlots * S.Bpad * 8);
         const size_t o_stage = take((size_t)n * B * 8), o_stage2 = take((size_t)m * B * 8), o_stage3 = take((size_t)m * B * 8);
         const size_t o_dd = take((size_t)B * kNormChunks * 2 * sizeof(DD)), o_norms = take((size_t)6 * S.Bpad * 8);
+        const size_t o_raw = take(layout == 1 ? (size_t)n * B * 8 : 8);
         char *base = static_cast<char *>(pool_alloc_zeroed(off, actual.device_number, st));
         S.arena = base;
         double **nv[9] = {&S.X, &S.X_hat, &S.X_bar, &S.DX, &S.Z_bar, &S.lastX, &S.C, &S.L, &S.U};
@@ -790,7 +815,16 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         S.d_stage = reinterpret_cast<double *>(base + o_stage); S.d_stage2 = reinterpret_cast<double *>(base + o_stage2);
         S.d_stage3 = reinterpret_cast<double *>(base + o_stage3);
         S.d_dd = reinterpret_cast<DD *>(base + o_dd); S.d_norms = reinterpret_cast<double *>(base + o_norms);
+        S.d_raw = reinterpret_cast<double *>(base + o_raw);
     }
+    // host array (rows x B values) -> column-major staging buffer on the device
+    auto stage_in = [&](double *dst, const double *host, int rows) {
+        const size_t bytes = sizeof(double) * (size_t)rows * B;
+        if (layout == 0) { h2d_large(dst, host, bytes, st); return; }
+        h2d_large(S.d_raw, host, bytes, st);
+        rowmajor_to_colmajor_kernel<<<dim3((rows + 31) / 32, (B + 31) / 32), 256, 0, st>>>(S.d_raw, dst, rows, B);
+        S.launches++;
+    };
     S.h_scal_doubles = (size_t)kMaxSlots * S.Bpad;
     S.h_scal = bpinned_acquire(S.h_scal_doubles);
 
@@ -801,8 +835,8 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     const dim3 tgrid_n((n + 31) / 32, S.G), tgrid_m((m + 31) / 32, S.G);
     double *dn = S.d_norms;   // rows of Bpad: 0 norm_b_org, 1 b_scale, 2 norm_c_org, 3 c_scale, 4 norm_b, 5 norm_c
     // rows first: b_scale is needed by l and u
-    h2d_large(S.d_stage2, AL_in, sizeof(double) * (size_t)m * B, st);
-    h2d_large(S.d_stage3, AU_in, sizeof(double) * (size_t)m * B, st);
+    stage_in(S.d_stage2, AL_in, m);
+    stage_in(S.d_stage3, AU_in, m);
     batched_scale_rows_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage2, S.d_stage3, S.eng.row_norm, m, S.d_dd);
     batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 2, B, S.Bpad, dn, 0x3, bc ? 0 : 0x2);
     batched_div_rows_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage2, S.d_stage3, dn + S.Bpad, bc, m, S.d_dd);
@@ -810,16 +844,16 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     to_group_layout_scaled_kernel<-1, false><<<tgrid_m, 256, 0, st>>>(S.d_stage2, S.AL, m, B, nullptr, nullptr, false);
     to_group_layout_scaled_kernel<1, false><<<tgrid_m, 256, 0, st>>>(S.d_stage3, S.AU, m, B, nullptr, nullptr, false);
     // cost
-    h2d_large(S.d_stage, C_in, sizeof(double) * (size_t)n * B, st);
+    stage_in(S.d_stage, C_in, n);
     batched_scale_cols_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage, S.eng.col_norm, n, S.d_dd);
     batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 2, B, S.Bpad, dn + 2 * (size_t)S.Bpad, 0x3, bc ? 0 : 0x2);
     batched_div_cols_kernel<<<norm_grid, kBThreads, 0, st>>>(S.d_stage, dn + 3 * (size_t)S.Bpad, bc, n, S.d_dd);
     batched_norm_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(S.d_dd, 1, B, S.Bpad, dn + 5 * (size_t)S.Bpad, 0, 0);
     to_group_layout_scaled_kernel<0, false><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.C, n, B, nullptr, nullptr, false);
     // bounds on x: l, u *= col_norm, /= b_scale, +-inf -> +-1e100
-    h2d_large(S.d_stage, l_in, sizeof(double) * (size_t)n * B, st);
+    stage_in(S.d_stage, l_in, n);
     to_group_layout_scaled_kernel<-1, true><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.L, n, B, S.eng.col_norm, dn + S.Bpad, bc);
-    h2d_large(S.d_stage, u_in, sizeof(double) * (size_t)n * B, st);
+    stage_in(S.d_stage, u_in, n);
     to_group_layout_scaled_kernel<1, true><<<tgrid_n, 256, 0, st>>>(S.d_stage, S.U, n, B, S.eng.col_norm, dn + S.Bpad, bc);
     S.launches += 13;
     {
@@ -1077,6 +1111,25 @@ extern "C" HPRLP_batched_results solve_batched(const LP_info_cpu *model, int bat
     int ng = 1;
     if (const char *e = getenv("HPRLP_NUM_GPUS")) ng = std::max(1, atoi(e));
     return hprlp_b200_solve_batched_multi(model, batch_size, C_in, AL_in, AU_in, l_in, u_in, obj_constants, param, ng);
+}
+
+// solve_batched for callers that hold the five dense inputs ROW-major, i.e. as C-ordered (n, B) / (m, B) arrays -- what the
+// reference's Python API takes (bindings/python/src/hprlp_pybind.cpp:413-455 re-packs them element by element on the
+// host before every call: SURVEY.md 8f rank 4).  Here the arrays are uploaded as they are and re-laid out on the device.
+// layout: 0 = column-major (same as solve_batched), 1 = row-major.  Outputs are column-major as in solve_batched.
+extern "C" HPRLP_batched_results hprlp_b200_solve_batched_layout(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C_in,
+                                                                  const HPRLP_FLOAT *AL_in, const HPRLP_FLOAT *AU_in,
+                                                                  const HPRLP_FLOAT *l_in, const HPRLP_FLOAT *u_in,
+                                                                  const HPRLP_FLOAT *obj_constants, const HPRLP_parameters *param,
+                                                                  int layout) {
+    if (!model || !model->A || batch_size <= 0 || !C_in || !AL_in || !AU_in || !l_in || !u_in || layout < 0 || layout > 1) {
+        return make_batched_error("ERROR", model ? model->m : 0, model ? model->n : 0, std::max(batch_size, 0));
+    }
+    return abi_guard<HPRLP_batched_results>("hprlp_b200_solve_batched_layout", [&]() -> HPRLP_batched_results {
+        HPRLP_parameters def;
+        const HPRLP_parameters base = param ? *param : def;
+        return solve_batched_on_device(model, batch_size, C_in, AL_in, AU_in, l_in, u_in, obj_constants, &base, layout);
+    }, [&] { return make_batched_error("ERROR", model->m, model->n, batch_size); });
 }
 
 extern "C" void free_batched_results(HPRLP_batched_results *results) {   // reference :1094-1105

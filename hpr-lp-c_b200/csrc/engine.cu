@@ -19,7 +19,6 @@
 #include <mutex>
 #include <thread>
 
-#define HPR_SET_TEX(op, t) op.tex = t;
 
 namespace hpr {
 
@@ -439,6 +438,14 @@ static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
     dispatch_cold(view_of(M), M.G, op, st);
 }
 
+// out = M g over the hot dispatch (power iteration, partitioned x-side pass); tex = g as a texture, or 0
+template <bool DOTS>
+static void launch_spmv_hot(const DevCsr &M, const double *g, cudaTextureObject_t tex, double *out, const double *q, double *partials,
+                            cudaStream_t st) {
+    if (tex) { SpmvOp<DOTS, true> o; o.g = g; o.tex = tex; o.out = out; o.q = q; o.partials = partials; launch_stream_hot(M, o, st); }
+    else     { SpmvOp<DOTS, false> o; o.g = g; o.tex = 0; o.out = out; o.q = q; o.partials = partials; launch_stream_hot(M, o, st); }
+}
+
 // One device arena per engine: a single cudaMalloc + one zero-fill instead of ~45 cudaMalloc/cudaMemset/cudaFree
 // pairs (cudaMalloc/cudaFree of multi-GB buffers are synchronous and cost tens of ms each on the e2e path).
 struct Arena { char *base = nullptr; size_t size = 0, off = 0; };
@@ -667,7 +674,11 @@ void Engine::alloc_common() {
     d_scal = dalloc<double>(16);
     h_scal = pinned_block_acquire();      // 16 residual / reduction scalars
     h_params = h_scal + 16;               // 4 sigma parameters (same recycled pinned block)
-    auto make_tex = [](double *ptr, size_t count) {
+    int tex_limit = 0;   // linear textures hold at most this many (8-byte) elements; longer vectors are gathered with ld.global.nc
+    HPR_CUDA_CHECK(cudaDeviceGetAttribute(&tex_limit, cudaDevAttrMaxTexture1DLinearWidth, device));
+    if (const char *e = getenv("HPRLP_TEX_LIMIT")) tex_limit = atoi(e);   // tests: force the non-texture variants
+    auto make_tex = [tex_limit](double *ptr, size_t count) -> cudaTextureObject_t {
+        if (count > (size_t)tex_limit) return 0;
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ptr;
         rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = count * sizeof(double);
         cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
@@ -683,11 +694,11 @@ void Engine::alloc_common() {
 
 // Host -> device copy of a large PAGEABLE array.  cudaMemcpyAsync from pageable memory is staged by the driver through one
 // pinned buffer by one thread (~10-12 GB/s measured on the B200 boxes: 0.1 s for the 1.2 GB matrix of C3, most of the
-// e2e setup time).  Here kUpThreads host threads each stage their slice through two recycled 8 MB pinned buffers on their
+// e2e setup time).  Here kUpThreads (8) host threads each stage their slice through two recycled 8 MB pinned buffers on their
 // own stream (memcpy of chunk k+1 overlaps the DMA of chunk k).  The staging buffers live for the process (like the pinned
 // scalar blocks); a second concurrent upload (partitioned mode: one host thread per GPU) falls back to the plain copy.
 namespace {
-constexpr int kUpThreads = 4;
+constexpr int kUpThreads = 8;
 constexpr size_t kUpChunk = (size_t)8 << 20;
 std::mutex g_stage_mu;
 char *g_stage[kUpThreads][2] = {};
@@ -1060,6 +1071,27 @@ void Engine::scale(const HPRLP_parameters *p) {
 // ------------------------------------------------------------------------------------------------
 // power iteration (reference src/power_iteration.cu:20-119)
 // ------------------------------------------------------------------------------------------------
+// First-solve warm-up (api.cu, hprlp_b200_warmup): creating the CUDA context (~0.3-2 s with the module load) and loading
+// cuRAND's device code (~0.6-1.2 s for the first generator on B200) are paid once per process.  Both can run on a second
+// host thread while this one parses the MPS file or runs the PSLP presolve.  Errors are ignored here -- the real calls
+// report them.
+void warm_device(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaFree(nullptr);   // context + module load
+    double *buf = nullptr;
+    if (cudaMalloc(&buf, 2 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+    curandGenerator_t gen = nullptr;
+    if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) == CURAND_STATUS_SUCCESS) {
+        curandSetPseudoRandomGeneratorSeed(gen, 1ULL);
+        curandGenerateNormalDouble(gen, buf, 2, 0.0, 1.0);
+        cudaDeviceSynchronize();
+        curandDestroyGenerator(gen);
+    }
+    cudaFree(buf);
+    try { engine_pool(device); } catch (...) {}
+    cudaGetLastError();
+}
+
 void Engine::power_start_vector(double *d_z) {
     // cuRAND XORWOW (CURAND_RNG_PSEUDO_DEFAULT), seed 1, N(0,1), then + 1e-8.  For odd m the reference's
     // unchecked curandGenerateNormalDouble fails with LENGTH_NOT_MULTIPLE and leaves z = 0 (its Ax
@@ -1117,11 +1149,9 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     int it;
     for (it = 1; it <= max_iter; ++it) {
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
-        SpmvOp<false, true> o1; o1.g = q; o1.tex = tex_q; o1.out = atq; o1.q = nullptr; o1.partials = nullptr;
-        launch_stream_hot(AT, o1, stream);
+        launch_spmv_hot<false>(AT, q, tex_q, atq, nullptr, nullptr, stream);
         allreduce(atq, n);   // A^T q = sum over row blocks
-        SpmvOp<true, true> o2; o2.g = atq; o2.tex = tex_atq; o2.out = z; o2.q = q; o2.partials = d_partials;
-        launch_stream_hot(A, o2, stream);
+        launch_spmv_hot<true>(A, atq, tex_atq, z, q, d_partials, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
         allreduce(d_scal, 2);
         launches += 4;
@@ -1171,6 +1201,28 @@ void Engine::upload_params() {   // reference reset_/upload_halpern_*_params, sr
 
 void Engine::reset_halpern_counter() { HPR_CUDA_CHECK(cudaMemsetAsync(d_k, 0, 2 * sizeof(int), stream)); }
 
+// The two fused passes of one HPR iteration.  Gathers go through the TEX pipe when the gathered vector could be bound as
+// a linear texture (alloc_common), through ld.global.nc otherwise.
+void Engine::launch_x_phase(bool check) {
+    auto go = [&](auto ox) {
+        ox.y = y; ox.tex = tex_y; ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
+        ox.x_bar = check ? x_bar : nullptr; ox.z_bar = check ? z_bar : nullptr; ox.x_tmp = check ? x_tmp : nullptr;
+        ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
+        launch_stream_hot(AT, ox, stream);
+    };
+    if (tex_y) { if (check) go(XPhaseOp<true, true>()); else go(XPhaseOp<false, true>()); }
+    else       { if (check) go(XPhaseOp<true, false>()); else go(XPhaseOp<false, false>()); }
+}
+void Engine::launch_y_phase(bool check) {
+    auto go = [&](auto oy) {
+        oy.x_hat = x_hat; oy.tex = tex_xhat; oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
+        oy.y_bar = check ? y_bar : nullptr; oy.y_obj = check ? y_obj : nullptr; oy.y_tmp = check ? y_tmp : nullptr;
+        oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
+        launch_stream_hot(A, oy, stream);
+    };
+    if (tex_xhat) { if (check) go(YPhaseOp<true, true>()); else go(YPhaseOp<false, true>()); }
+    else          { if (check) go(YPhaseOp<true, false>()); else go(YPhaseOp<false, false>()); }
+}
 // wn holds this rank's partial A_p^T y_p.  On return x (owned block) is updated and x_hat is complete on every rank.
 void Engine::exchange_x(bool check) {
     const int gx = vec_grid(xb1 - xb0);
@@ -1211,42 +1263,14 @@ void Engine::launch_iteration(bool check) {
         // Row-partitioned iteration: partial w_p = A_p^T y_p over the local rows, reduce-scatter so that this
         // GPU holds (A^T y) on ITS x-block, x-update on that block only, all-gather of the x_hat blocks, then the fused
         // y-phase on the local rows of A with the full x_hat.
-        SpmvOp<false, true> ow; ow.g = y; ow.tex = tex_y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
-        launch_stream_hot(AT, ow, stream);
+        launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream);
         exchange_x(check);
-        if (check) {
-            YPhaseOp<true> oy;
-            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
-            oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
-            launch_stream_hot(A, oy, stream);
-        } else {
-            YPhaseOp<false> oy;
-            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
-            oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
-            launch_stream_hot(A, oy, stream);
-        }
+        launch_y_phase(check);
         launches += 2;
         return;
     }
-    if (check) {
-        XPhaseOp<true> ox;
-        ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
-        ox.x_bar = x_bar; ox.z_bar = z_bar; ox.x_tmp = x_tmp; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
-        launch_stream_hot(AT, ox, stream);
-        YPhaseOp<true> oy;
-        oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
-        oy.y_bar = y_bar; oy.y_obj = y_obj; oy.y_tmp = y_tmp; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
-        launch_stream_hot(A, oy, stream);
-    } else {
-        XPhaseOp<false> ox;
-        ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
-        ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
-        launch_stream_hot(AT, ox, stream);
-        YPhaseOp<false> oy;
-        oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
-        oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
-        launch_stream_hot(A, oy, stream);
-    }
+    launch_x_phase(check);
+    launch_y_phase(check);
     launches += 2;
 }
 
@@ -1468,25 +1492,14 @@ double Engine::time_phase_ms(int which, int reps) {
     HPR_CUDA_CHECK(cudaEventCreate(&e0));
     HPR_CUDA_CHECK(cudaEventCreate(&e1));
     auto one = [&]() {
-        if (which == 0) {
-            XPhaseOp<false> ox;
-            ox.y = y; HPR_SET_TEX(ox, tex_y) ox.x = x; ox.x_hat = x_hat; ox.c = c; ox.l = l; ox.u = u; ox.x0 = x0;
-            ox.x_bar = nullptr; ox.z_bar = nullptr; ox.x_tmp = nullptr; ox.params = d_params; ox.kx = d_k; ox.ky = d_k + 1;
-            launch_stream_hot(AT, ox, stream);
-        } else if (which == 2) {   // row-partitioned x-side pass: partial w_p = A_p^T y_p
-            SpmvOp<false, true> ow; ow.g = y; ow.tex = tex_y; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
-            launch_stream_hot(AT, ow, stream);
-        } else if (which == 3) {   // row-partitioned x-update on the owned block (from whatever wn holds)
+        if (which == 0) launch_x_phase(false);
+        else if (which == 2) launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream);   // row-partitioned x-side pass
+        else if (which == 3)   // row-partitioned x-update on the owned block (from whatever wn holds)
             x_update_kernel<false><<<vec_grid(xb1 - xb0), kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
-        } else if (which == 4) {   // the two exchanges of one iteration, as the loop issues them
+        else if (which == 4) {   // the exchange of one iteration, as the loop issues it
             if (coll && px) exchange_x(false);   // peer-memory path: the exchange IS the fused x-update kernel
             else if (coll) { coll->reduce_scatter_inplace(wn, xblock, stream); coll->all_gather_inplace(x_hat, xblock, stream); }
-        } else {
-            YPhaseOp<false> oy;
-            oy.x_hat = x_hat; HPR_SET_TEX(oy, tex_xhat) oy.y = y; oy.AL = AL; oy.AU = AU; oy.y0 = y0;
-            oy.y_bar = nullptr; oy.y_obj = nullptr; oy.y_tmp = nullptr; oy.params = d_params; oy.ky = d_k + 1; oy.kx = d_k;
-            launch_stream_hot(A, oy, stream);
-        }
+        } else launch_y_phase(false);
         launches++;
     };
     one();
@@ -1658,6 +1671,15 @@ bool Engine::solve_advance(const HPRLP_parameters *param, SolveHooks *hooks, int
             long long ne = std::min(nper, nprint);
             if ((long long)param->max_iter > iter) ne = std::min(ne, (long long)param->max_iter);
             if (pause_at > iter) ne = std::min(ne, (long long)pause_at);
+            // TIME_LIMIT: the reference looks at the clock every iteration (src/HPRLP.cu:184-198).  Launches are asynchronous
+            // here, so the run to the next visited index is capped by what the remaining time allows at the rate measured
+            // so far; at that index the clock is read again (after the residual fetch has synchronised).
+            if (iter > 0 && param->time_limit < 1e9) {
+                const double per_iter = elapsed / iter;
+                const double left = param->time_limit - elapsed;
+                const long long fit = per_iter > 0 ? (long long)std::max(1.0, std::min(left / per_iter + 1.0, 2.0e9)) : 1;
+                ne = std::min(ne, (long long)iter + std::max<long long>(fit, 1));
+            }
             next_event = (int)std::min<long long>(ne, INT32_MAX);
         }
         // iterations iter .. next_event-1: the last one is a check iteration when the reference's

@@ -130,6 +130,8 @@ class Engine {
     void upload_params();
     void reset_halpern_counter();
     void launch_iteration(bool check);
+    void launch_x_phase(bool check);
+    void launch_y_phase(bool check);
     void run_normal(int count);            // count normal iterations (CUDA-graph replay)
     void compute_residuals(int iter, bool compute_gap, Residuals *res, RestartState *rs);
     double weighted_norm_after_restart();
@@ -223,6 +225,7 @@ void fill_b200_info(const Engine &eng, const SolveHooks &h, hprlp_b200_info *inf
 
 // device memory pool of the engines, staged copies of large pageable arrays (engine.cu)
 void release_cached_device_memory();
+void warm_device(int device);   // first-solve warm-up: context, modules, cuRAND (errors ignored)
 void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st);
 void pool_free(void *p, cudaStream_t st);
 void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // src may be reused on return; dst is stream-ordered

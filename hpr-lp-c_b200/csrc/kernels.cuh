@@ -389,7 +389,8 @@ struct OpBase {
 // update_zx_check_kernel :203-226):  w = (A^T y)_j ; zt = x + sigma (w - c) ; x_bar = proj_[l,u] zt ;
 // x_hat = 2 x_bar - x ; x <- f2 x_hat + f1 x0 ; check also stores x_bar, z_bar=(x_bar-zt)/sigma, x_bar-x_hat.
 // Halpern counter: this kernel reads k from kx and mirrors it into ky for the y-phase.
-template <bool CHECK>
+// TEX: gathers through the TEX pipe (y bound as a linear texture); false: ld.global.nc (vectors beyond the texture size limit)
+template <bool CHECK, bool TEX = true>
 struct XPhaseOp : OpBase {
     const double *y;
     double *x, *x_hat;
@@ -414,8 +415,8 @@ struct XPhaseOp : OpBase {
         const int2 t = tex1Dfetch<int2>(tex, col);
         return __hiloint2double(t.y, t.x);
     }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER == 1 ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER >= 1 ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const {
         const double xi = x[j];
         const double zt = fma(sigma, acc[0] - c[j], xi);
@@ -435,7 +436,7 @@ struct XPhaseOp : OpBase {
 // v = (A x_hat)_i - lambda sigma y ; d = max(AL - v, min(AU - v, 0)) ; y_bar = d/(lambda sigma) ;
 // y_hat = 2 y_bar - y ; y <- f2 y_hat + f1 y0 ; check also stores y_bar, y_obj = v + d, y_bar - y_hat.
 // Advances the Halpern counter: kx <- ky + 1 (reference advance_halpern_factors_kernel :192-200).
-template <bool CHECK>
+template <bool CHECK, bool TEX = true>
 struct YPhaseOp : OpBase {
     const double *x_hat;
     double *y;
@@ -459,8 +460,8 @@ struct YPhaseOp : OpBase {
         const int2 t = tex1Dfetch<int2>(tex, col);
         return __hiloint2double(t.y, t.x);
     }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER == 1 ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * (HPR_TEX_GATHER >= 1 ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
         const double yi = y[i];
         const double v = fma(-lamsig, yi, acc[0]);

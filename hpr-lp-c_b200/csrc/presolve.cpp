@@ -8,12 +8,21 @@
 //
 // Differences from the reference bridge, by design: PSLP runs in-process (the reference forks a worker and ships
 // the reduced CSR through pipes, :628-700); the calls, settings, reduced-model construction, postsolve and the
-// printed original-space KKT validation (:499-624) are the same.
+// printed original-space KKT validation (:499-624) are the same.  Running in-process is what lets solve() bring up
+// the CUDA context and cuRAND on a second thread under the presolve (api.cu, warm_start).
+// Crash isolation: the reference gets it from the fork -- a PSLP crash kills the worker and solve() falls back to the
+// original model (:677-691).  Here the PSLP calls run inside run_guarded(): SIGSEGV / SIGBUS / SIGFPE / SIGABRT raised
+// on the presolving thread are caught and turned into the same fallback (the presolver object is abandoned, never
+// touched again).  Faults on PSLP's own worker threads, or memory corruption that surfaces later, are not recoverable
+// this way -- a weaker guarantee than a separate process, stated here rather than hidden.
 #include <chrono>
 #include <cmath>
+#include <csetjmp>
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/hprlp_b200.h"
@@ -41,6 +50,40 @@ struct Handle {
     int rm = 0, rn = 0;
 };
 
+// ---- synchronous-fault guard around the third-party calls ---------------------------------------------------------
+thread_local sigjmp_buf *t_guard = nullptr;   // non-null while THIS thread is inside a guarded PSLP call
+void fault_handler(int sig) {
+    if (t_guard) siglongjmp(*t_guard, sig);
+    std::signal(sig, SIG_DFL);   // not ours (another thread, or outside a guarded region): default action
+    std::raise(sig);
+}
+// Runs body() (plain C calls only: a non-local jump skips no destructors).  Returns 0, or the signal that aborted it.
+template <class F>
+int run_guarded(F &&body) {
+    static std::mutex mu;   // signal dispositions are process-wide: one guarded region at a time
+    std::lock_guard<std::mutex> lk(mu);
+    static const int sigs[4] = {SIGSEGV, SIGBUS, SIGFPE, SIGABRT};
+    struct sigaction sa, old[4];
+    std::memset(&sa, 0, sizeof(sa));
+    sa.sa_handler = fault_handler;
+    sa.sa_flags = SA_NODEFER;
+    sigemptyset(&sa.sa_mask);
+    for (int i = 0; i < 4; ++i) sigaction(sigs[i], &sa, &old[i]);
+    sigjmp_buf jb;
+    const int caught = sigsetjmp(jb, 1);
+    if (caught == 0) {
+        t_guard = &jb;
+        if (const char *e = std::getenv("HPRLP_TEST_PRESOLVE_FAULT")) {   // tests: a fault inside the guarded region
+            if (std::strcmp(e, "abort") == 0) std::abort();
+            std::raise(SIGSEGV);
+        }
+        body();
+    }
+    t_guard = nullptr;
+    for (int i = 0; i < 4; ++i) sigaction(sigs[i], &old[i], nullptr);
+    return caught;
+}
+
 template <typename T>
 T *dup_array(const T *src, size_t count) {
     T *p = static_cast<T *>(std::malloc(sizeof(T) * (count ? count : 1)));
@@ -61,8 +104,19 @@ bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_in
     h->stg->verbose = false;   // reference src/pslp_integration.cpp:231-234
     if (param && std::isfinite(param->time_limit) && param->time_limit > 0.0)
         h->stg->max_time = std::min(h->stg->max_time, static_cast<double>(param->time_limit));
-    h->pre = new_presolver(model->A->value, model->A->colIndex, model->A->rowPtr, (size_t)model->m, (size_t)model->n,
-                           (size_t)model->A->numElements, model->AL, model->AU, model->l, model->u, model->c, h->stg);
+    Settings *stg = h->stg;
+    Presolver *volatile pre = nullptr;   // written inside the guarded region, read after a possible siglongjmp
+    const int fault = run_guarded([&] {
+        pre = new_presolver(model->A->value, model->A->colIndex, model->A->rowPtr, (size_t)model->m, (size_t)model->n,
+                            (size_t)model->A->numElements, model->AL, model->AU, model->l, model->u, model->c, stg);
+        if (pre) run_presolver(pre);
+    });
+    if (fault) {   // PSLP crashed: abandon its state (never freed, never touched) and solve the original model
+        std::fprintf(stderr, "[warn] PSLP presolve crashed (signal %d); solving original model\n", fault);
+        delete h;
+        return false;
+    }
+    h->pre = pre;
     auto fail = [&](const char *msg) {
         std::fprintf(stderr, "[warn] %s; solving original model\n", msg);
         if (h->pre) free_presolver(h->pre);
@@ -71,7 +125,6 @@ bool presolve_run(const LP_info_cpu *model, const HPRLP_parameters *param, LP_in
         return false;
     };
     if (!h->pre) return fail("PSLP presolver could not be created");
-    run_presolver(h->pre);
     std::printf("PSLP presolve time: %g seconds\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     PresolvedProblem *rp = h->pre->reduced_prob;
     if (!rp) return fail("PSLP did not return a reduced problem");
@@ -162,7 +215,18 @@ void presolve_postsolve(HPRLP_results *result, const LP_info_cpu *original, void
     Handle *h = static_cast<Handle *>(handle);
     std::printf("\n================================================================================\nPSLP POSTSOLVE\n"
                 "================================================================================\n");
-    postsolve(h->pre, result->x, result->y, result->z);
+    Presolver *pre = h->pre;
+    double *rx = result->x, *ry = result->y, *rz = result->z;
+    const int fault = run_guarded([&] { postsolve(pre, rx, ry, rz); });
+    if (fault) {   // no original-space solution can be recovered: report it (the reference's worker would have died too)
+        std::fprintf(stderr, "[error] PSLP postsolve crashed (signal %d)\n", fault);
+        h->pre = nullptr;   // abandoned
+        std::free(result->x); std::free(result->y); std::free(result->z);
+        result->x = result->y = result->z = nullptr;
+        std::memset(result->status, 0, sizeof(result->status));
+        std::strncpy(result->status, "ERROR", sizeof(result->status) - 1);
+        return;
+    }
     const Solution *sol = h->pre->sol;
     if (!sol || (int)sol->dim_x != original->n || (int)sol->dim_y != original->m) {
         std::fprintf(stderr, "[warn] PSLP postsolve returned inconsistent solution dimensions\n");

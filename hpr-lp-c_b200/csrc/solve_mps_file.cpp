@@ -14,6 +14,7 @@
 #include <string>
 
 #include "../../include/HPRLP.h"
+#include "../../include/hprlp_b200.h"
 
 namespace {
 
@@ -92,6 +93,7 @@ int main(int argc, char **argv) {
         usage(argv[0]);
         return 1;
     }
+    hprlp_b200_warmup(param.device_number);   // CUDA context + cuRAND come up while the MPS file is parsed
     LP_info_cpu *model = create_model_from_mps(input.c_str());
     if (!model) {
         std::fprintf(stderr, "Failed to load model from MPS file: %s\n", input.c_str());

@@ -73,6 +73,15 @@ HPRLP_batched_results hprlp_b200_solve_batched_multi(const LP_info_cpu *model, i
                                                      const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
                                                      const HPRLP_parameters *param, int n_gpus);
 
+/* solve_batched for dense inputs held ROW-major (layout 1: C-ordered (n, B) / (m, B) arrays, element (i, k) at i*B + k),
+ * as the reference's Python API receives them; layout 0 = column-major = solve_batched.  The arrays are uploaded as they
+ * are and re-laid out on the device: no host-side re-packing (reference bindings/python/src/hprlp_pybind.cpp:343-356,
+ * 413-455 copies all five arrays element by element before every call).  Outputs column-major as in solve_batched. */
+HPRLP_batched_results hprlp_b200_solve_batched_layout(const LP_info_cpu *model, int batch_size, const HPRLP_FLOAT *C,
+                                                      const HPRLP_FLOAT *AL, const HPRLP_FLOAT *AU, const HPRLP_FLOAT *l,
+                                                      const HPRLP_FLOAT *u, const HPRLP_FLOAT *obj_constants,
+                                                      const HPRLP_parameters *param, int layout);
+
 /* One LP row-block partitioned over n_gpus GPUs of one node (devices param->device_number ...).  GPU p owns a block of
  * rows of A (+ its transpose, y-side vectors) and the x-block J_p.  Per iteration: partial A_p^T y_p -> NCCL
  * reduce-scatter over NVLink -> x-update on J_p -> NCCL all-gather of x_hat -> fused y-phase on the local rows;
@@ -129,6 +138,12 @@ void hprlp_b200_presolve_free(void *handle, LP_info_cpu *reduced);
  * HPRLP_POOL_RETAIN_MB, default 8192) so that repeated solve() calls skip cudaMalloc/cudaFree.  This call returns all
  * cached memory to the driver (cudaMemPoolTrimTo 0).  The reference frees everything at the end of each solve. */
 void hprlp_b200_release_cached_memory(void);
+
+/* First solve of a process: CUDA context creation, module load and cuRAND's first generator cost 1-3 s, more than a
+ * whole configs[1] solve.  This call starts them on a background thread and returns immediately, so they overlap host
+ * work that precedes the solve (MPS parsing in build/solve_mps_file; the PSLP presolve inside solve(), which starts the
+ * warm-up itself).  The next solve on `device` joins the thread.  HPRLP_NO_WARMUP=1 disables it. */
+void hprlp_b200_warmup(int device);
 
 /* cudaProfilerStart/Stop of the library's (statically linked) CUDA runtime: lets `ncu --profile-from-start off`
  * capture only the timed region of bench.py. */

@@ -73,3 +73,24 @@ def test_sharded_equals_unsharded_single_gpu(pkg, engine):
     else:   # shards see the same matrix scaling / lambda_max; instances are independent
         for k in ("x", "y", "z"):
             assert np.max(np.abs(a[k] - b[k])) <= 1e-9 * max(1.0, np.max(np.abs(a[k])))
+
+
+def test_row_major_inputs_need_no_host_repacking(pkg, engine):
+    """the reference's Python API takes C, l, u as (n, B) and AL, AU as (m, B) arrays and re-packs them
+    element by element on the host before every solve_batched call (bindings/python/src/hprlp_pybind.cpp:343-356,413-455).
+    hprlp_b200_solve_batched_layout(layout=1) takes the C-ordered arrays as they are and re-lays them out on the device:
+    results are bit-identical to the column-major entry."""
+    base, d, _ = make_batch(pkg, 300, 1000, 4500, 37)
+    p = pkg.Parameters.default(stop_tol=1e-6, use_presolve=False)
+    model = engine.create_model(base)
+    ref = engine.solve_batched(model, d["C"], d["AL"], d["AU"], d["l"], d["u"], None, p)                 # (B, n) C-ordered = column-major ABI
+    nB = {k: np.ascontiguousarray(v.T) for k, v in d.items()}                                               # (n, B) C-ordered: the Python API's arrays
+    assert all(a.flags.c_contiguous and not a.flags.f_contiguous for a in nB.values())
+    got = engine.solve_batched_nB(model, nB["C"], nB["AL"], nB["AU"], nB["l"], nB["u"], None, p)
+    fort = engine.solve_batched_nB(model, *[np.asfortranarray(nB[k]) for k in ("C", "AL", "AU", "l", "u")], None, p)
+    engine.free_model(model)
+    for out in (got, fort):
+        assert out["status"] == ref["status"] and np.array_equal(out["iter"], ref["iter"])
+        assert out["x"].shape == (1000, 37) and out["y"].shape == (300, 37)
+        for k in ("x", "y", "z"):
+            assert np.array_equal(out[k], ref[k].T), k

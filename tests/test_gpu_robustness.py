@@ -79,3 +79,35 @@ def test_lookback_bitwise_reproducible_under_concurrency(pkg, engine):
             for k in "xyz":
                 assert np.array_equal(o[k], solo[k]), k
     engine.free_model(model)
+
+
+def test_vectors_beyond_the_texture_limit_use_plain_gathers(pkg, engine, monkeypatch):
+    """Gathered vectors longer than cudaDevAttrMaxTexture1DLinearWidth cannot be bound as linear textures; the engine then
+    dispatches the ld.global.nc variants of the same kernels.  HPRLP_TEX_LIMIT=0 forces them: same bits."""
+    lp = pkg.synth_lp("powerlaw", 4000, 12000, 200000)
+    p = pkg.Parameters.default(use_presolve=False, max_iter=300, stop_tol=1e-30)
+    model = engine.create_model(lp)
+    a = engine.solve(model, p, main=True)
+    monkeypatch.setenv("HPRLP_TEX_LIMIT", "0")
+    b = engine.solve(model, p, main=True)
+    engine.free_model(model)
+    assert a["status"] == b["status"] and a["iter"] == b["iter"]
+    for k in "xyz":
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_time_limit_is_honoured_between_checks(pkg, engine):
+    """The reference looks at the clock every iteration (src/HPRLP.cu:184-198); here the run to the next residual check is
+    capped by what the remaining time allows, so a solve stops close to time_limit even when checks are 150 iterations apart."""
+    import time
+    lp = pkg.synth_lp("uniform", 100_000, 400_000, 8_000_000)
+    model = engine.create_model(lp)
+    engine.solve(model, pkg.Parameters.default(use_presolve=False, max_iter=20, stop_tol=1e-30), main=True)   # warm
+    p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-30, time_limit=0.25, check_iter=100000)
+    t0 = time.perf_counter()
+    r = engine.solve(model, p, main=True)
+    wall = time.perf_counter() - t0
+    engine.free_model(model)
+    assert r["status"] == "TIME_LIMIT"
+    assert 0.25 <= r["time"] < 0.6, r["time"]          # not tens of thousands of iterations later
+    assert wall < 3.0

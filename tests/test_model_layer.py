@@ -1,6 +1,8 @@
 """CPU: host model layer (create_model_from_arrays / create_model_from_mps / CSC conversion /
 transpose order).  When the reference's own build is present (oracle/_ref) the LP_info_cpu arrays
 are compared bit-exactly against it ("MPS parsing, CSR/CSC construction ... bit-exact")."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -318,3 +320,29 @@ def test_csc_input_multithreaded_conversion_bit_exact(engine, reference, pkg):
     for other in ("ref_csc", "ours_csr"):
         for k in got["ours_csc"]:
             assert np.array_equal(np.asarray(got["ours_csc"][k]), np.asarray(got[other][k])), (other, k)
+
+
+@pytest.mark.parametrize("fault", ["segv", "abort"])
+def test_presolve_crash_falls_back_to_original_model(pkg, engine, monkeypatch, fault):
+    """The reference runs PSLP in a forked worker, so a presolver crash only loses the presolve
+    (src/pslp_integration.cpp:677-691).  Here PSLP runs in-process inside a signal guard: a synchronous fault on the
+    presolving thread must come back as "presolve failed" (the caller then solves the original model), not kill the
+    process.  HPRLP_TEST_PRESOLVE_FAULT raises the fault inside the guarded region."""
+    lp = pkg.synth_lp("uniform", 60, 150, 600)
+    p = pkg.Parameters.default()
+    model = engine.create_model(lp)
+    engine.lib.hprlp_b200_presolve.argtypes = [C.POINTER(pkg.LPInfoCpu), C.POINTER(pkg.Parameters), C.POINTER(pkg.LPInfoCpu), C.POINTER(C.c_void_p)]
+    engine.lib.hprlp_b200_presolve_free.argtypes = [C.c_void_p, C.POINTER(pkg.LPInfoCpu)]
+    red, h = pkg.LPInfoCpu(), C.c_void_p()
+    if not engine.lib.hprlp_b200_presolve(model, C.byref(p), C.byref(red), C.byref(h)):
+        engine.free_model(model)
+        pytest.skip("PSLP not linked into this build of libhprlp.so")
+    engine.lib.hprlp_b200_presolve_free(h, C.byref(red))
+    monkeypatch.setenv("HPRLP_TEST_PRESOLVE_FAULT", fault)
+    red, h = pkg.LPInfoCpu(), C.c_void_p()
+    assert engine.lib.hprlp_b200_presolve(model, C.byref(p), C.byref(red), C.byref(h)) == 0     # survived, reported failure
+    monkeypatch.delenv("HPRLP_TEST_PRESOLVE_FAULT")
+    red, h = pkg.LPInfoCpu(), C.c_void_p()
+    assert engine.lib.hprlp_b200_presolve(model, C.byref(p), C.byref(red), C.byref(h)) == 1     # and the bridge still works
+    engine.lib.hprlp_b200_presolve_free(h, C.byref(red))
+    engine.free_model(model)
