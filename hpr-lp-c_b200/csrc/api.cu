@@ -275,8 +275,6 @@ int hprlp_b200_scale_only(const LP_info_cpu *lp, const HPRLP_parameters *param_i
     Engine eng;
     eng.upload(lp, param->device_number);
     eng.scale(param);
-    eng.set_item_order(eng.A, false);    // hand the matrices back in logical CSR order
-    eng.set_item_order(eng.AT, false);
     const int m = eng.m, n = eng.n;
     const size_t nnz = (size_t)eng.nnz;
     auto d2h = [&](void *dst, const void *src, size_t bytes) {

@@ -872,9 +872,6 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     const double power_start = now_s();
     S.lambda_max = S.eng.power_iteration(5000, 1.0e-4, nullptr, nullptr) * 1.01;
     const double power_time = now_s() - power_start;
-    // the batched kernels index A and A^T as plain CSR: leave the single-instance kernels' item order
-    S.eng.set_item_order(S.eng.A, false);
-    S.eng.set_item_order(S.eng.AT, false);
 
     RestartHost R;
     R.restart_flag.assign(B, 0); R.first_restart.assign(B, 1); R.inner.assign(B, 0); R.times.assign(B, 0);

@@ -372,35 +372,49 @@ static CsrView<int> view_of(const DevCsr &M) {
     CsrView<int> v;
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
-    v.flags = M.flags; v.head_part = M.head_part; v.tail_part = M.tail_part; v.ticket = M.ticket;
+    v.head_part = M.head_part; v.tail_part = M.tail_part; v.ticket = M.ticket;
     v.carry_in = nullptr; v.carry_out = nullptr;
     return v;
 }
 
-template <class Op>
+template <class Op, int G>
 static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
     constexpr size_t bytes = stream_smem_bytes<Op>();
     static std::atomic<unsigned> configured{0};   // per instantiation, one bit per device (function attributes are per device)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!(configured.load() & (1u << dev))) {
-        HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         if (const char *e = getenv("HPRLP_CARVEOUT"))   // tuning hook: shared-memory carve-out in percent
-            HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, int>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+            HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         configured.fetch_or(1u << dev);
     }
-    csr_stream_kernel<Op, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
+    csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
 }
-// (r1 dispatched on the lanes-per-row parameter G here; the segmented reduction of r2 has one variant per op)
+
 template <class Op>
-static void dispatch_hot(const CsrView<int> &v, int, const Op &op, cudaStream_t st) { launch_one<Op>(v, op, st); }
+static void dispatch_hot(const CsrView<int> &v, int G, const Op &op, cudaStream_t st) {
+    switch (G) {
+        case 1:  launch_one<Op, 1>(v, op, st); break;
+        case 2:  launch_one<Op, 2>(v, op, st); break;
+        case 4:  launch_one<Op, 4>(v, op, st); break;
+        case 8:  launch_one<Op, 8>(v, op, st); break;
+        case 16: launch_one<Op, 16>(v, op, st); break;
+        default: launch_one<Op, 32>(v, op, st); break;
+    }
+}
+// setup / check-iteration passes: fewer instantiations
 template <class Op>
-static void dispatch_cold(const CsrView<int> &v, int, const Op &op, cudaStream_t st) { launch_one<Op>(v, op, st); }
+static void dispatch_cold(const CsrView<int> &v, int G, const Op &op, cudaStream_t st) {
+    if (G <= 2)      launch_one<Op, 1>(v, op, st);
+    else if (G <= 8) launch_one<Op, 4>(v, op, st);
+    else             launch_one<Op, 16>(v, op, st);
+}
 // A pass over a column-banded matrix: one launch per band, row sums carried from band to band, the op's epilogue (and its
 // reductions) only in the last one.  The gathered slice of every launch fits the L2.
 template <class Op, bool HOT>
 static void launch_banded(const DevCsr &M, const Op &op, cudaStream_t st) {
-    static_assert(!Op::kMax, "banded passes carry one sum per row");
+    static_assert(Op::NV == 1 && !Op::kMax, "banded passes carry one sum per row");
     const int nb = (int)M.bands.size();
     for (int b = 0; b < nb; ++b) {
         CsrView<int> v = view_of(M.bands[b]);
@@ -411,14 +425,14 @@ static void launch_banded(const DevCsr &M, const Op &op, cudaStream_t st) {
 }
 template <class Op>
 static void launch_stream_hot(const DevCsr &M, const Op &op, cudaStream_t st) {
-    if constexpr (!Op::kMax) {
+    if constexpr (Op::NV == 1 && !Op::kMax) {
         if (!M.bands.empty()) { launch_banded<Op, true>(M, op, st); return; }
     }
     dispatch_hot(view_of(M), M.G, op, st);
 }
 template <class Op>
 static void launch_stream(const DevCsr &M, const Op &op, cudaStream_t st) {
-    if constexpr (!Op::kMax) {
+    if constexpr (Op::NV == 1 && !Op::kMax) {
         if (!M.bands.empty()) { launch_banded<Op, false>(M, op, st); return; }
     }
     dispatch_cold(view_of(M), M.G, op, st);
@@ -544,15 +558,27 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.val = dalloc<double>(padded);
     const size_t witems = (size_t)M.n_items * kWarps;   // warp items (n_items = CTAs)
     M.item_row = dalloc<int>(witems + 1);
-    M.flags = dalloc<unsigned char>(witems * 32);
-    M.head_part = dalloc<PartSlot>(witems);   // all-ones = "not published" (set in finish_matrix); consumers re-arm what they read
-    M.tail_part = dalloc<PartSlot>(witems);
+    M.head_part = dalloc<PartSlot>(witems * 2);   // all-ones = "not published" (set in finish_matrix); consumers re-arm what they read
+    M.tail_part = dalloc<PartSlot>(witems * 2);
     M.ticket = dalloc<unsigned long long>(1);
 }
 static void free_matrix(DevCsr &M) {
-    dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row); dfree(M.flags);
+    dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
     dfree(M.head_part); dfree(M.tail_part); dfree(M.ticket);
     M = DevCsr();
+}
+
+static int pick_lanes(double mean_len, const char *env_name) {
+    if (const char *e = getenv(env_name)) {
+        const int g = atoi(e);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
+    }
+    // Lanes per row from the measured mean row length of this matrix.  Every extra lane costs shuffle
+    // wavefronts on the L1 data stage (the binding unit), so few lanes win: B200 sweep on C2/C3
+    // (gpurun_out_14/15): mean 10 and 20 -> 1 lane best; mean 50 and 100 -> 8 lanes best (4 and 16 within 3 %).
+    if (mean_len < 28.0) return 1;
+    if (mean_len < 40.0) return 4;
+    return 8;
 }
 
 void Engine::finish_matrix(DevCsr &M) {
@@ -560,28 +586,11 @@ void Engine::finish_matrix(DevCsr &M) {
     const int entries = M.n_items * kWarps + 1;
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
-    const size_t witems = (size_t)M.n_items * kWarps;
-    HPR_CUDA_CHECK(cudaMemsetAsync(M.flags, 0, witems * 32, stream));
-    build_row_flags_kernel<int><<<(M.rows + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, reinterpret_cast<unsigned *>(M.flags));
-    launches++;
-    M.item_order = false;          // the arrays were just filled in logical CSR order (upload / transposition / band split)
-    set_item_order(M, true);
-    const size_t part_bytes = sizeof(PartSlot) * witems;
+    const size_t part_bytes = sizeof(PartSlot) * (size_t)M.n_items * kWarps * 2;
     HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0xFF, part_bytes, stream));   // every packet "not published"
     HPR_CUDA_CHECK(cudaMemsetAsync(M.tail_part, 0xFF, part_bytes, stream));
     HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned long long), stream));
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
-}
-
-void Engine::set_item_order(DevCsr &M, bool on) {
-    if (M.item_order == on) return;
-    const long long witems = (long long)M.n_items * kWarps;
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((witems + wpb - 1) / wpb);
-    if (on) permute_items_kernel<true><<<grid, 32 * wpb, 0, stream>>>(M.col, M.val, witems);
-    else permute_items_kernel<false><<<grid, 32 * wpb, 0, stream>>>(M.col, M.val, witems);
-    launches++;
-    M.item_order = on;
 }
 
 // Column bands of M for passes whose gathered vector (M.cols doubles) does not fit the L2: 8-byte gathers from DRAM run at
@@ -599,11 +608,10 @@ void Engine::build_bands(DevCsr &M) {
     HPR_CUDA_CHECK(cudaMalloc(&brp, sizeof(int) * stride * nb));
     HPR_CUDA_CHECK(cudaMemsetAsync(brp, 0, sizeof(int) * stride * nb, stream));
     std::vector<long long> bn(nb, 0);
-    set_item_order(M, false);   // the band split reads the entries in logical CSR order
     band_count(M.rows, M.rowPtr, M.col, (int)band_cols, nb, brp, bn.data(), stream);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t total = 0;
-    std::vector<size_t> o_col(nb), o_val(nb), o_item(nb), o_head(nb), o_tail(nb), o_tick(nb), o_flag(nb);
+    std::vector<size_t> o_col(nb), o_val(nb), o_item(nb), o_head(nb), o_tail(nb), o_tick(nb);
     std::vector<int> items(nb);
     for (int b = 0; b < nb; ++b) {
         items[b] = std::max(1, (int)((bn[b] + kChunk - 1) / kChunk));
@@ -611,9 +619,8 @@ void Engine::build_bands(DevCsr &M) {
         o_col[b] = total;  total += up(padded * sizeof(int));
         o_val[b] = total;  total += up(padded * sizeof(double));
         o_item[b] = total; total += up((wit + 1) * sizeof(int));
-        o_head[b] = total; total += up(wit * sizeof(PartSlot));
-        o_tail[b] = total; total += up(wit * sizeof(PartSlot));
-        o_flag[b] = total; total += up(wit * 32);
+        o_head[b] = total; total += up(wit * 2 * sizeof(PartSlot));
+        o_tail[b] = total; total += up(wit * 2 * sizeof(PartSlot));
         o_tick[b] = total; total += up(sizeof(unsigned long long));
     }
     const size_t o_carry = total; total += up((size_t)M.rows * sizeof(double));
@@ -633,15 +640,16 @@ void Engine::build_bands(DevCsr &M) {
         Bd.head_part = reinterpret_cast<PartSlot *>(store + o_head[b]);
         Bd.tail_part = reinterpret_cast<PartSlot *>(store + o_tail[b]);
         Bd.ticket = reinterpret_cast<unsigned long long *>(store + o_tick[b]);
-        Bd.flags = reinterpret_cast<unsigned char *>(store + o_flag[b]);
         ptrs[b] = Bd.col; ptrs[nb + b] = Bd.val;
     }
     HPR_CUDA_CHECK(cudaMemcpyAsync(store + o_ptrs, ptrs.data(), sizeof(void *) * 2 * nb, cudaMemcpyHostToDevice, stream));
     band_fill(M.rows, M.rowPtr, M.col, M.val, (int)band_cols, nb, brp, reinterpret_cast<int *const *>(store + o_ptrs),
               reinterpret_cast<double *const *>(store + o_ptrs) + nb, stream);
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // ptrs (host vector) must outlive the copy
-    set_item_order(M, true);
-    for (int b = 0; b < nb; ++b) finish_matrix(M.bands[b]);
+    for (int b = 0; b < nb; ++b) {
+        finish_matrix(M.bands[b]);
+        M.bands[b].G = pick_lanes(M.bands[b].mean_len, "HPRLP_LANES_BAND");
+    }
     M.carry = reinterpret_cast<double *>(store + o_carry);
     M.band_store = store;
     M.band_rowptr_store = brp;
@@ -680,6 +688,8 @@ void Engine::alloc_common() {
     };
     tex_y = make_tex(y, m); tex_xhat = make_tex(x_hat, n);
     tex_q = make_tex(wm2, m); tex_atq = make_tex(wn, n);   // power iteration: q and A^T q
+    A.G = pick_lanes(A.mean_len, "HPRLP_LANES_A");
+    AT.G = pick_lanes(AT.mean_len, "HPRLP_LANES_AT");
 }
 
 // Host -> device copy of a large PAGEABLE array.  cudaMemcpyAsync from pageable memory is staged by the driver through one
@@ -809,11 +819,6 @@ void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st) {
     HPR_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
     return p;
 }
-void *pool_alloc_raw(size_t bytes, int device, cudaStream_t st) {   // stream-ordered, not zeroed; release with cudaFreeAsync
-    void *p = nullptr;
-    HPR_CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), engine_pool(device), st));
-    return p;
-}
 void pool_free(void *p, cudaStream_t st) {
     if (!p) return;
     static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
@@ -867,7 +872,7 @@ void Engine::prepare(int m_, int n_, long long nnz_, int dev) {
         size_t need = 0;
         for (size_t rows : {(size_t)m, (size_t)n})
             need += arena_round((rows + 1) * 4) + arena_round(padded * 4) + arena_round(padded * 8) + arena_round((witems + 1) * 4) +
-                    2 * arena_round(witems * sizeof(PartSlot)) + arena_round(witems * 32) + arena_round(8);
+                    2 * arena_round(witems * 2 * sizeof(PartSlot)) + arena_round(8);
         need += 10 * arena_round((size_t)m * 8) + 13 * arena_round((dist() ? npad : (size_t)n) * 8);
         need += arena_round((size_t)(ctas + witems / kWarps + kVecBlocks + 64) * kMaxSlots * 8) + (1u << 16);
         Arena *ar = new Arena;
@@ -1333,17 +1338,18 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(AT), 5, d_scal);
     }
     auto fill_primal = [&](auto &o) {
-        o.x_bar = x_bar; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
-        o.y_bar = y_bar; o.partials = d_partials;
+        o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
+        o.y_bar = y_bar; o.y_tmp = y_tmp; o.partials = d_partials;
     };
     {
-        ResidualPrimalOp o; fill_primal(o); launch_stream(A, o, stream);
-        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal + 5);
+        ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 4, d_scal + 5);
         launches += 4;
     }
     if (compute_gap) {
-        // restart gap terms <A dx, dy>, |dy|^2 (slots 7, 8) as a second single-product pass (r1 measured a fused
-        // two-product variant at 4.5 ms on C3 against 0.6 ms per single-product pass: two gathers per nonzero).
+        // restart gap terms <A dx, dy>, |dy|^2 (slots 7, 8) as a second single-product pass.  The two-product variant
+        // (ResidualPrimalOp<true>) doubles the shared-memory staging; at 6 CTAs/SM that leaves ~28 KB of L1, i.e. hardly any
+        // in-flight gather misses: measured 4.5 ms on C3 against 0.6 ms per single-product pass (same row sums bit for bit).
         WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
         launch_stream(A, o, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal + 7);

@@ -41,12 +41,10 @@ struct DevCsr {
     int *col = nullptr;     // padded to n_items * kChunk
     double *val = nullptr;  // padded likewise
     int *item_row = nullptr;
-    unsigned char *flags = nullptr;   // row-start bits per lane of every warp item (kernels.cuh, build_row_flags_kernel)
-    bool item_order = false;          // col/val currently stored in the lane-contiguous item order (kernels.cuh, item_slot)
     int n_items = 0;
     PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries (all-ones = empty)
     unsigned long long *ticket = nullptr;   // chunk tickets handed out by csr_stream_kernel over all launches (kernels.cuh)
-    int G = 0;              // (r1: lanes per row in phase 2; the r2 segmented reduction has no such parameter)
+    int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
     // Column bands (Engine::build_bands): when the gathered vector is larger than the L2 can hold, the passes over this
@@ -188,9 +186,6 @@ class Engine {
    private:
     void alloc_common();
     void finish_matrix(DevCsr &M);
-   public:
-    void set_item_order(DevCsr &M, bool on);   // switch col/val between logical CSR order and the kernels' item order
-   private:
     void build_bands(DevCsr &M);
     void fetch_scalars(int count);
     std::map<int, cudaGraphExec_t> graphs_;
@@ -233,7 +228,6 @@ void release_cached_device_memory();
 void warm_device(int device);   // first-solve warm-up: context, modules, cuRAND (errors ignored)
 void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st);
 void pool_free(void *p, cudaStream_t st);
-void *pool_alloc_raw(size_t bytes, int device, cudaStream_t st);
 void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // src may be reused on return; dst is stream-ordered
 void d2h_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // returns when the copy is complete
 

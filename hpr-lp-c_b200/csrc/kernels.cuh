@@ -10,19 +10,13 @@
 //           there is no CTA barrier on the path (one at kernel entry only), every warp of an SM is at a different point of
 //           its item, which is what hides the HBM/L2 latency of the gathers (r1 v1 used CTA-wide
 //           items + __syncthreads and was latency-bound: profiles/r1_v1_ncu_full_c2_details.txt).
-//   layout  inside an item the col/val arrays are stored LANE-CONTIGUOUS (r2 v5): the 128-bit / 64-bit coalesced loads
-//           of lane t (positions (u*32 + t)*2 + h, u = 0..3) deliver the 8 CONSECUTIVE nonzeros 8t .. 8t+7 of the item.
-//           The permutation is applied in place on the device once per matrix (permute_items_kernel); everything that
-//           indexes nonzeros logically goes through item_slot().
-//   phase 1 the warp streams its nonzeros (double2 values, int2 column indices, evict-first), gathers the dense vector
-//           through the TEX pipe (L2 resident) and multiplies: 8 products per lane, in registers.
-//   phase 2 (r2 v5) every lane sums its own products row segment by row segment -- a per-lane byte of row-start flags
-//           (precomputed from rowPtr, 1 bit per nonzero) says where a row begins; segments that span lanes are closed by
-//           one segmented warp scan (5 shuffle steps).  Only ONE value per row segment goes through shared memory (the
-//           segment total, picked up by the lane that runs the row's epilogue) instead of one store + one load per
-//           nonzero as in r1: ~13 instead of 256 shared-memory stores per item on a 20-nonzeros-per-row matrix.  The
-//           fused epilogue (projection, dual update, Halpern averaging, residual terms ...) runs lane-parallel over
-//           consecutive rows with coalesced vector loads/stores, as before.
+//   phase 1  the warp streams its nonzeros with 128-bit/64-bit coalesced loads (double2 values,
+//           int2 column indices, evict-first), gathers the dense vector through the read-only path
+//           (L2 resident) and stores the products in its private slice of shared memory.
+//   phase 2  G lanes per row (G chosen per matrix from the mean row length) sum the row's slice of
+//           the product array; the row totals are handed to one lane per row, so that the fused
+//           epilogue (projection, dual update, Halpern averaging, residual terms ...) runs
+//           lane-parallel over consecutive rows with coalesced vector loads/stores.
 //   rows cut by an item boundary: every item but the last one of the row publishes its partial sum as one
 //           8-byte packet (an aligned 64-bit relaxed store: single-copy atomic, so the value IS the ready flag --
 //           an all-ones NaN pattern that no arithmetic produces means "not published"); the warp whose item
@@ -76,13 +70,12 @@ struct CsrView {
     int rows;
     long long nnz;
     const RP *rowPtr;
-    const int *col;       // padded to a multiple of kChunk (pad: col 0, value 0); lane-contiguous item order (item_slot)
+    const int *col;       // padded to a multiple of kChunk (pad: col 0, value 0)
     const double *val;    // padded likewise
     const int *item_row;  // n_ctas*kWarps + 1 entries: first row finalised by warp item i
     int n_items;          // CTAs in the grid
-    const unsigned char *flags;   // [items * 32] row-start bits of lane t of item i at flags[i*32 + t] (build_row_flags_kernel)
-    PartSlot *head_part;  // [items] partial of the row entering the item from the left (and leaving it to the right)
-    PartSlot *tail_part;  // [items] partial of the row that starts in the item and leaves it to the right
+    PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
+    PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
     unsigned long long *ticket;   // chunk tickets handed out so far over ALL launches on this matrix (never reset: every
                                   // launch has exactly n_items CTAs and each takes one, so chunk = ticket % n_items)
     // Column-banded matrices (engine.cu, build_bands): a pass over the matrix is one launch per band; every band but the
@@ -161,91 +154,44 @@ template <bool MAX>
 __device__ __forceinline__ double combine(double a, double b) { return MAX ? fmax(a, b) : a + b; }
 
 // ------------------------------------------------------------------------------------------------
-// Lane-contiguous item layout: logical nonzero k (0..255) of an item is stored at slot item_slot(k), so that the
-// coalesced vector loads of lane t (double2 / int2 at index u*32 + t, u = 0..3) return nonzeros 8t .. 8t+7.
-// ------------------------------------------------------------------------------------------------
-static_assert(kLaneNnz == 8, "item layout is written for 8 nonzeros per lane");
-__host__ __device__ __forceinline__ int item_slot(int k) { return ((((k & 7) >> 1) * 32 + (k >> 3)) << 1) | (k & 1); }
-__host__ __device__ __forceinline__ int item_logical(int p) { return (((p >> 1) & 31) << 3) | (((p >> 1) >> 5) << 1) | (p & 1); }
-// position in the stored (permuted) arrays of logical nonzero q of the whole matrix
-__host__ __device__ __forceinline__ long long stored_pos(long long q) { return (q & ~(long long)(kWarpChunk - 1)) + item_slot((int)(q & (kWarpChunk - 1))); }
-
-// In-place switch of one matrix between the logical CSR order and the lane-contiguous item order; one warp per item.
-template <bool TO_ITEM_ORDER>
-__global__ void permute_items_kernel(int *col, double *val, long long n_witems) {
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= n_witems) return;
-    int *c = col + item * kWarpChunk;
-    double *v = val + item * kWarpChunk;
-    int cc[kLaneNnz];
-    double vv[kLaneNnz];
-#pragma unroll
-    for (int j = 0; j < kLaneNnz; ++j) {   // slot read by this lane -> slot written by this lane (a bijection on 0..255)
-        const int k = lane * kLaneNnz + j;
-        const int src = TO_ITEM_ORDER ? k : item_slot(k);
-        cc[j] = c[src];
-        vv[j] = v[src];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < kLaneNnz; ++j) {
-        const int k = lane * kLaneNnz + j;
-        const int dst = TO_ITEM_ORDER ? item_slot(k) : k;
-        c[dst] = cc[j];
-        v[dst] = vv[j];
-    }
-}
-
-// Row-start flags: bit (q & 7) of flags[q >> 3] is set iff a NONEMPTY row starts at logical nonzero q.  flags[item*32 + t]
-// is therefore the byte of lane t of that item.  (flags zeroed before; words are updated with atomicOr.)
-template <typename RP>
-__global__ void build_row_flags_kernel(const RP *rowPtr, int rows, unsigned *flag_words) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const long long q = (long long)rowPtr[r];
-    if ((long long)rowPtr[r + 1] <= q) return;
-    const long long byte = q >> 3;
-    atomicOr(flag_words + (byte >> 2), 1u << (((int)(byte & 3) << 3) + (int)(q & 7)));
-}
-
-// ------------------------------------------------------------------------------------------------
 // The streaming skeleton.  Op supplies:
+//   static constexpr int NV      number of product streams (1 or 2)
 //   static constexpr bool kMax   combine with fmax instead of +
 //   void init()                  per-thread scalar loads
-//   double elem(v, col)          per-nonzero term (elem_b: the same for the second nonzero of a pair)
-//   void row(r, acc, p0, p1)     fused epilogue of a complete row
-//   void finish(scratch, block)  CTA-level reductions (may be empty)
-// Dynamic shared memory: kWarps * kSegStride doubles (row-segment totals) + reduction scratch.
+//   void elem(v, col, out[NV])   per-nonzero term
+//   void row(r, acc[NV], p0, p1) fused epilogue of a complete row
+//   void finish(scratch)         CTA-level reductions (may be empty)
+// Dynamic shared memory: kWarps * NV * kWarpChunk doubles (product slices) + reduction scratch.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSegStride = kWarpChunk + 8;   // up to kWarpChunk + 1 row segments per item (every nonzero its own row + the leading one)
 template <class Op>
 constexpr size_t stream_smem_bytes() {
-    return sizeof(double) * ((size_t)kWarps * kSegStride + (size_t)kMaxSlots * kWarps);
+    return sizeof(double) * ((size_t)kWarps * Op::NV * kWarpChunk + (size_t)kMaxSlots * kWarps);
 }
 
-template <class Op, typename RP>
+template <class Op, int G, typename RP>
 __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(CsrView<RP> M, Op op) {
+    constexpr int NV = Op::NV;
     constexpr bool MX = Op::kMax;
+    constexpr int RPR = 32 / G;   // rows per reduce round
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *seg = smem + (size_t)warp * kSegStride;                  // row-segment totals of this warp's item
-    double *red_scratch = smem + (size_t)kWarps * kSegStride;
-    __shared__ double own_part[kWarps];         // this item's share of the row it finishes
-    __shared__ PartSlot cta_part[kWarps * 2];   // [warp][head, tail]: partials handed to a later warp of this CTA
+    double *prod = smem + (size_t)warp * NV * kWarpChunk;            // [NV][kWarpChunk], private to this warp
+    double *red_scratch = smem + (size_t)kWarps * NV * kWarpChunk;
+    __shared__ double own_part[kWarps * 2];     // [warp][2]: this item's share of the row it finishes
+    __shared__ PartSlot cta_part[kWarps * 4];   // [warp][head, tail][2]: partials handed to a warp of this CTA
     __shared__ unsigned chunk_s;
     // The chunk this CTA works on comes from a ticket: chunks are handed out in the order CTAs START, so every item to
     // the left of ours belongs to a CTA that is already running (or done) -- the look-back below cannot wait for a CTA
     // that was never scheduled, whatever order the hardware dispatches blockIdx in.
     if (threadIdx.x == 0) chunk_s = (unsigned)(atomicAdd(M.ticket, 1ULL) % (unsigned long long)gridDim.x);
-    if (threadIdx.x < kWarps * 2) cta_part[threadIdx.x] = kPartEmpty;
+    if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
     const int chunk = (int)chunk_s;
 
     op.init();
-    auto complete_row = [&](int r, double t, long long q0, long long q1) {
-        if (M.carry_in) t += M.carry_in[r];
-        if (M.carry_out) M.carry_out[r] = t;
+    auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
+        if (M.carry_in) t[0] += M.carry_in[r];
+        if (M.carry_out) M.carry_out[r] = t[0];
         else op.row(r, t, q0, q1);
     };
     const int item = chunk * kWarps + warp;
@@ -254,78 +200,45 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     const long long s = (long long)item * kWarpChunk;
     const long long e = (s + kWarpChunk < M.nnz) ? s + kWarpChunk : (s < M.nnz ? M.nnz : s);
 
-    // row metadata of the first batch and the row-start flags: requested before the nonzeros so their latency overlaps phase 1
+    // row metadata of the first batch: requested before the nonzeros so its latency overlaps phase 1
     const int rA = __ldg(M.item_row + item);
     const int rB = __ldg(M.item_row + item + 1);
     const int r_last = (rB < M.rows) ? rB : M.rows - 1;   // last row touched (rB included: it may start here)
-    const unsigned f = __ldg(M.flags + (size_t)item * 32 + lane);   // bit j: a row starts at my nonzero j
     long long p0 = 0, p1 = 0;
     if (rA + lane <= r_last) {
         p0 = (long long)M.rowPtr[rA + lane];
         p1 = (long long)M.rowPtr[rA + lane + 1];
     }
 
-    // ---- phase 1: stream nonzeros, gather, multiply: 8 consecutive nonzeros of the item per lane, all loads in flight ------
-    double prod[kLaneNnz];
+    // ---- phase 1: stream nonzeros, gather, multiply (kRoundNnz loads in flight per lane) -----------
     {
         const double2 *v2 = reinterpret_cast<const double2 *>(M.val + s);
         const int2 *c2 = reinterpret_cast<const int2 *>(M.col + s);
-        double2 vv[kLaneNnz / 2];
-        int2 cc[kLaneNnz / 2];
 #pragma unroll
-        for (int u = 0; u < kLaneNnz / 2; ++u) {
-            cc[u] = ld_stream(c2 + u * 32 + lane);
-            vv[u] = ld_stream(v2 + u * 32 + lane);
+        for (int rd = 0; rd < kLaneNnz / kRoundNnz; ++rd) {
+            double2 vv[kRoundNnz / 2];
+            int2 cc[kRoundNnz / 2];
+#pragma unroll
+            for (int u = 0; u < kRoundNnz / 2; ++u) {
+                const int t = (rd * (kRoundNnz / 2) + u) * 32 + lane;
+                cc[u] = ld_stream(c2 + t);
+                vv[u] = ld_stream(v2 + t);
+            }
+#pragma unroll
+            for (int u = 0; u < kRoundNnz / 2; ++u) {
+                double o0[NV], o1[NV];
+                op.elem(vv[u].x, cc[u].x, o0);
+                op.elem_b(vv[u].y, cc[u].y, o1);
+                const int t = (rd * (kRoundNnz / 2) + u) * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < NV; ++q)
+                    *reinterpret_cast<double2 *>(prod + q * kWarpChunk + 2 * t) = make_double2(o0[q], o1[q]);
+            }
         }
-#pragma unroll
-        for (int u = 0; u < kLaneNnz / 2; ++u) {
-            prod[2 * u] = op.elem(vv[u].x, cc[u].x);
-            prod[2 * u + 1] = op.elem_b(vv[u].y, cc[u].y);
-        }
     }
-    if (e - s < kWarpChunk) {   // last item of the matrix (warp-uniform): padding slots contribute the identity
-#pragma unroll
-        for (int j = 0; j < kLaneNnz; ++j)
-            if (s + lane * kLaneNnz + j >= e) prod[j] = 0.0;
-    }
-
-    // ---- phase 2a: row-segment sums.  Segment 0 = nonzeros before the first row start of the item (the tail of a row
-    // that entered from the left, possibly empty); segment i >= 1 starts at the i-th row start.  A lane closes the
-    // segments that end inside it on its own; the ones that run across lanes are closed by a segmented scan.
-    int nf_before = 0;   // row starts in lower lanes
-#pragma unroll
-    for (int j = 0; j < kLaneNnz; ++j) nf_before += __popc(__ballot_sync(0xffffffffu, (f >> j) & 1u) & ((1u << lane) - 1u));
-    const bool has = f != 0u;
-    double acc = 0.0, head = 0.0;   // |a| >= 0, so 0 is also the identity of fmax here
-    int seen = 0;
-#pragma unroll
-    for (int j = 0; j < kLaneNnz; ++j) {
-        if ((f >> j) & 1u) {
-            if (seen == 0) head = acc;                 // end of the segment that entered this lane from the left
-            else seg[nf_before + seen] = acc;          // a segment that started at my previous row start: complete
-            acc = 0.0;
-            ++seen;
-        }
-        acc = combine<MX>(acc, prod[j]);
-    }
-    // inclusive segmented scan of the open right ends: S(t) = acc(t) [+ S(t-1) if lane t has no row start]
-    const unsigned hasmask = __ballot_sync(0xffffffffu, has);
-    double S = acc;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, S, off);
-        // lanes lane-off+1 .. lane must all be free of row starts for the two runs to belong to one segment
-        const bool join = lane >= off && ((hasmask >> (lane - off + 1)) & ((off == 32 ? 0u : (1u << off)) - 1u)) == 0u;
-        if (join) S = combine<MX>(up, S);
-    }
-    const double left = __shfl_up_sync(0xffffffffu, S, 1);
-    if (has) seg[nf_before] = combine<MX>(lane > 0 ? left : 0.0, head);   // the segment that ends at my first row start
-    if (lane == 31) seg[nf_before + seen] = S;                          // the last segment of the item
     __syncwarp();
 
-    // ---- phase 2b: lane-parallel epilogue over the rows of the item; a row's total is its segment's ----------------------
-    const int seg0 = (rA <= r_last && (long long)M.rowPtr[rA <= r_last ? rA : 0] < s) ? 0 : 1;   // does row rA enter from the left?
-    int seen_rows = 0;   // nonempty rows of the item in earlier batches
+    // ---- phase 2: row sums (G lanes per row) handed to one lane per row, lane-parallel epilogue ------
     for (int base = rA; base <= r_last; base += 32) {   // warp-uniform
         const int r = base + lane;
         const bool valid = r <= r_last;
@@ -333,30 +246,67 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
             p0 = 0; p1 = 0;
             if (valid) { p0 = (long long)M.rowPtr[r]; p1 = (long long)M.rowPtr[r + 1]; }
         }
-        bool nonempty = false;
+        int lo = 0, hi = 0;
         if (valid) {
             const long long a = p0 > s ? p0 : s;
             const long long b = p1 < e ? p1 : e;
-            nonempty = b > a;
+            if (b > a) { lo = (int)(a - s); hi = (int)(b - s); }
         }
-        const unsigned ne_mask = __ballot_sync(0xffffffffu, nonempty);
-        const double tot = nonempty ? seg[seg0 + seen_rows + __popc(ne_mask & ((1u << lane) - 1u))] : 0.0;
-        seen_rows += __popc(ne_mask);
+        const int nrows = min(32, r_last - base + 1);
+        double tot[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) tot[q] = 0.0;   // |a| >= 0, so 0 is also the identity of fmax here
+        if (G == 1) {
+            for (int k = lo; k < hi; ++k) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) tot[q] = combine<MX>(tot[q], prod[q * kWarpChunk + k]);
+            }
+        } else {
+            const int gl = lane & (G - 1), gid = lane / G;
+            const int rounds = (nrows + RPR - 1) / RPR;
+            for (int t = 0; t < rounds; ++t) {
+                const int o = t * RPR + gid;   // row (offset in the batch) reduced by my group this round
+                const int glo = __shfl_sync(0xffffffffu, lo, o);
+                const int ghi = __shfl_sync(0xffffffffu, hi, o);
+                double acc[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) acc[q] = 0.0;
+                for (int k = glo + gl; k < ghi; k += G) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) acc[q] = combine<MX>(acc[q], prod[q * kWarpChunk + k]);
+                }
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) acc[q] = combine<MX>(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], off));
+                }
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const double v = __shfl_sync(0xffffffffu, acc[q], (lane % RPR) * G);
+                    if (lane / RPR == t) tot[q] = v;   // lane L owns row L of the batch
+                }
+            }
+        }
 
-        // A row cut by an item boundary is finished by the item that holds its end (below);
+        // lane-parallel epilogue.  A row cut by an item boundary is finished by the item that holds its end (below);
         // the other items it spans only publish their partial sums.
         if (valid) {
-            const bool hd = (r == rA) && (p0 < s);     // row entered this item from the left (lane 0, first batch)
+            const bool head = (r == rA) && (p0 < s);   // row entered this item from the left (lane 0, first batch)
             const bool cont = (p1 > e);                // row continues to the right
-            if (!hd && !cont) {
+            if (!head && !cont) {
                 complete_row(r, tot, p0, p1);
-            } else if (hd && !cont) {                  // finished below; park this item's share (no live registers)
-                own_part[warp] = tot;
-            } else if (hd || p0 < e) {                 // (else: r == rB and it starts in a later item)
+            } else if (head && !cont) {                // finished below; park this item's share (no live registers)
+#pragma unroll
+                for (int q = 0; q < NV; ++q) own_part[warp * 2 + q] = tot[q];
+            } else if (head || p0 < e) {               // (else: r == rB and it starts in a later item)
                 if (p1 <= cta_end) {                   // finished by a later warp of this CTA
-                    part_publish_cta(cta_part + warp * 2 + (hd ? 0 : 1), tot);
+                    PartSlot *slot = cta_part + warp * 4 + (head ? 0 : 2);
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) part_publish_cta(slot + q, tot[q]);
                 } else {                               // finished by a later CTA
-                    part_publish((hd ? M.head_part : M.tail_part) + (size_t)item, tot);
+                    PartSlot *slot = (head ? M.head_part : M.tail_part) + (size_t)item * 2;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) part_publish(slot + q, tot[q]);
                 }
             }
         }
@@ -370,23 +320,36 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     if (rA <= r_last && P0 < s && P1 <= e) {
         __syncwarp();   // own_part written by lane 0 above
         const int ia = (int)(P0 / kWarpChunk), ib = item;
-        auto fetch = [&](int j, bool tail) -> double {   // partial of item j: same CTA -> shared, earlier CTA -> global
-            if (j >= cta_item0) return part_consume_cta(cta_part + (j - cta_item0) * 2 + (tail ? 1 : 0));
-            return part_consume((tail ? M.tail_part : M.head_part) + (size_t)j);
+        auto fetch = [&](int j, bool tail, int q) -> double {   // partial of item j: same CTA -> shared, earlier CTA -> global
+            if (j >= cta_item0) return part_consume_cta(cta_part + (j - cta_item0) * 4 + (tail ? 2 : 0) + q);
+            return part_consume((tail ? M.tail_part : M.head_part) + (size_t)j * 2 + q);
         };
-        double sum;
+        double sum[NV];
         if (ib - ia < kSeqPartials) {
-            const double v = (ia + lane < ib) ? fetch(ia + lane, lane == 0) : own_part[warp];
-            sum = __shfl_sync(0xffffffffu, v, 0);
-            for (int t = 1; t <= ib - ia; ++t) sum = combine<MX>(sum, __shfl_sync(0xffffffffu, v, t));
+            double v[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) v[q] = (ia + lane < ib) ? fetch(ia + lane, lane == 0, q) : own_part[warp * 2 + q];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = __shfl_sync(0xffffffffu, v[q], 0);
+            for (int t = 1; t <= ib - ia; ++t) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_sync(0xffffffffu, v[q], t));
+            }
         } else {
-            sum = 0.0;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) sum[q] = 0.0;
             for (int j = ia + lane; j <= ib; j += 32) {
-                const double v = (j == ib) ? own_part[warp] : fetch(j, j == ia);
-                sum = combine<MX>(sum, v);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const double v = (j == ib) ? own_part[warp * 2 + q] : fetch(j, j == ia, q);
+                    sum[q] = combine<MX>(sum[q], v);
+                }
             }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sum = combine<MX>(sum, __shfl_xor_sync(0xffffffffu, sum, off));
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
+            }
         }
         if (lane == 0) complete_row(rA, sum, P0, P1);
     }
@@ -416,6 +379,7 @@ __global__ void build_item_rows_kernel(const RP *rowPtr, int rows, long long nnz
 // Ops
 // ================================================================================================
 struct OpBase {
+    static constexpr int NV = 1;
     static constexpr bool kMax = false;
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ void finish(double *, int) {}
@@ -451,11 +415,11 @@ struct XPhaseOp : OpBase {
         const int2 t = tex1Dfetch<int2>(tex, col);
         return __hiloint2double(t.y, t.x);
     }
-    __device__ __forceinline__ double elem(double v, int col) const { return v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ void row(int j, double acc0, long long, long long) const {
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const {
         const double xi = x[j];
-        const double zt = fma(sigma, acc0 - c[j], xi);
+        const double zt = fma(sigma, acc[0] - c[j], xi);
         const double xb = fmin(u[j], fmax(l[j], zt));
         const double xh = 2.0 * xb - xi;
         x[j] = fma(f2, xh, f1 * x0[j]);
@@ -496,11 +460,11 @@ struct YPhaseOp : OpBase {
         const int2 t = tex1Dfetch<int2>(tex, col);
         return __hiloint2double(t.y, t.x);
     }
-    __device__ __forceinline__ double elem(double v, int col) const { return v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
-    __device__ __forceinline__ void row(int i, double acc0, long long, long long) const {
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
         const double yi = y[i];
-        const double v = fma(-lamsig, yi, acc0);
+        const double v = fma(-lamsig, yi, acc[0]);
         const double d = fmax(AL[i] - v, fmin(AU[i] - v, 0.0));
         const double yb = inv_lamsig * d;
         const double yh = 2.0 * yb - yi;
@@ -525,11 +489,11 @@ struct ResidualDualOp : OpBase {
 #pragma unroll
         for (int s = 0; s < 5; ++s) t[s] = 0.0;
     }
-    __device__ __forceinline__ double elem(double v, int col) const { return v * __ldg(y_bar + col); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int j, double acc0, long long, long long) {
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(y_bar + col); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) {
         const double cj = c[j], zb = z_bar[j], xb = x_bar[j], cn = col_norm[j];
-        const double rd = (cj - acc0 - zb) * cn;
+        const double rd = (cj - acc[0] - zb) * cn;
         t[0] += rd * rd;
         t[1] += cj * xb;
         t[2] += xb * zb;
@@ -544,22 +508,31 @@ struct ResidualDualOp : OpBase {
     __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<5>(t, partials, scratch, block); }
 };
 
-// Primal residual pass over A (reference residual_compute_Rp_cusparse, src/main_iterate.cu:207-215):
-// slots 0 |Rp|^2, 1 <y_obj,y_bar>.  (The restart-gap terms <A x_tmp, y_tmp>, |y_tmp|^2 of :245-254 are a second
-// single-product pass, WeightedNormOp.)
+// Primal residual pass over A (reference residual_compute_Rp_cusparse, src/main_iterate.cu:207-215,
+// plus the restart-gap SpMV/dots :245-254): slots 0 |Rp|^2, 1 <y_obj,y_bar>, 2 <A x_tmp, y_tmp>, 3 |y_tmp|^2.
+template <bool GAP>
 struct ResidualPrimalOp : OpBase {
-    const double *x_bar, *AL, *AU, *row_norm, *y_obj, *y_bar;
+    static constexpr int NV = GAP ? 2 : 1;
+    const double *x_bar, *x_tmp, *AL, *AU, *row_norm, *y_obj, *y_bar, *y_tmp;
     double *partials;
-    double t[2];
-    __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ double elem(double v, int col) const { return v * __ldg(x_bar + col); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int i, double ax, long long, long long) {
+    double t[4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) t[s] = 0.0;
+    }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[NV]) const {
+        o[0] = v * __ldg(x_bar + col);
+        if (GAP) o[NV - 1] = v * __ldg(x_tmp + col);
+    }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[NV]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[NV], long long, long long) {
+        const double ax = acc[0];
         const double rp = fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax) * row_norm[i];
         t[0] += rp * rp;
         t[1] += y_obj[i] * y_bar[i];
+        if (GAP) { const double dy = y_tmp[i]; t[2] += acc[NV - 1] * dy; t[3] += dy * dy; }
     }
-    __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<2>(t, partials, scratch, block); }
+    __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<4>(t, partials, scratch, block); }
 };
 
 // M-norm cross term after a restart iteration (reference compute_weighted_norm,
@@ -569,11 +542,11 @@ struct WeightedNormOp : OpBase {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ double elem(double v, int col) const { return v * __ldg(dx + col); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int i, double acc0, long long, long long) {
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(dx + col); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) {
         const double d = dy[i];
-        t[0] += acc0 * d;
+        t[0] += acc[0] * d;
         t[1] += d * d;
     }
     __device__ __forceinline__ void finish(double *scratch, int block) { block_reduce_store<2>(t, partials, scratch, block); }
@@ -590,17 +563,18 @@ struct SpmvOp : OpBase {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ double elem(double v, int col) const {
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const {
         if (TEX) {
             const int2 w = tex1Dfetch<int2>(tex, col);
-            return v * __hiloint2double(w.y, w.x);
+            o[0] = v * __hiloint2double(w.y, w.x);
+        } else {
+            o[0] = v * __ldg(g + col);
         }
-        return v * __ldg(g + col);
     }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int i, double acc0, long long, long long) {
-        out[i] = acc0;
-        if (DOTS) { t[0] += acc0 * acc0; t[1] += q[i] * acc0; }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) {
+        out[i] = acc[0];
+        if (DOTS) { t[0] += acc[0] * acc[0]; t[1] += q[i] * acc[0]; }
     }
     __device__ __forceinline__ void finish(double *scratch, int block) {
         if (DOTS) block_reduce_store<2>(t, partials, scratch, block);
@@ -614,11 +588,11 @@ template <bool MAX, bool RAW>
 struct RowNormOp : OpBase {
     static constexpr bool kMax = MAX;
     double *out;
-    __device__ __forceinline__ double elem(double v, int) const { return fabs(v); }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int i, double acc0, long long, long long) const {
-        if (RAW) { out[i] = acc0; return; }
-        double r = sqrt(acc0);
+    __device__ __forceinline__ void elem(double v, int, double (&o)[1]) const { o[0] = fabs(v); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
+        if (RAW) { out[i] = acc[0]; return; }
+        double r = sqrt(acc[0]);
         if (r < 1e-15) r = 1.0;
         out[i] = r;
     }
@@ -631,14 +605,14 @@ struct CurtisReidOp : OpBase {
     const double *other;
     double *out;
     double *cnt_out;
-    __device__ __forceinline__ double elem(double v, int col) const {
-        return -log(fmax(fabs(v), 1e-300)) - __ldg(other + col);
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const {
+        o[0] = -log(fmax(fabs(v), 1e-300)) - __ldg(other + col);
     }
-    __device__ __forceinline__ double elem_b(double v, int col) const { return elem(v, col); }
-    __device__ __forceinline__ void row(int i, double acc0, long long p0, long long p1) const {
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long p0, long long p1) const {
         const long long cnt = p1 - p0;
-        if (RAW) { out[i] = acc0; cnt_out[i] = (double)cnt; return; }
-        out[i] = cnt > 0 ? acc0 / (double)cnt : 0.0;
+        if (RAW) { out[i] = acc[0]; cnt_out[i] = (double)cnt; return; }
+        out[i] = cnt > 0 ? acc[0] / (double)cnt : 0.0;
     }
 };
 
@@ -668,11 +642,9 @@ scale_values_kernel(CsrView<RP> M, double *val_rw, const double *rowfac, const d
         for (long long k = a + gl; k < b; k += GG) rf[(int)(k - s)] = f;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < kChunk; t += kThreads) {   // t = stored slot; the row factor is indexed by the logical position
-        const int lt = (t & ~(kWarpChunk - 1)) + item_logical(t & (kWarpChunk - 1));
-        if (s + lt >= e) continue;
+    for (int t = threadIdx.x; t < (int)(e - s); t += kThreads) {
         double v = val_rw[s + t];
-        const double fr = rf[lt];
+        const double fr = rf[t];
         const double fg = __ldg(gathfac + M.col[s + t]);
         const double f1 = ROW_FIRST ? fr : fg;
         const double f2 = ROW_FIRST ? fg : fr;

@@ -206,95 +206,3 @@ def test_model_is_sensitive_to_the_boundary_rule():
                 caught += 1
                 break
     assert caught > 0
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# r2 v5: lane-contiguous item layout + segmented reduction (kernels.cuh phase 2a / 2b), restated index for index
-# ---------------------------------------------------------------------------------------------------------------------
-def item_slot(k):
-    return ((((k & 7) >> 1) * 32 + (k >> 3)) << 1) | (k & 1)
-
-
-def item_logical(p):
-    return (((p >> 1) & 31) << 3) | (((p >> 1) >> 5) << 1) | (p & 1)
-
-
-def test_item_slot_is_a_bijection_that_makes_lane_loads_contiguous():
-    slots = [item_slot(k) for k in range(256)]
-    assert sorted(slots) == list(range(256))
-    assert all(item_logical(item_slot(k)) == k for k in range(256))
-    for lane in range(32):          # lane t loads (double2 / int2) index u*32 + t, u = 0..3  ->  elements 2*(u*32+t) + h
-        got = sorted(item_logical(2 * (u * 32 + lane) + h) for u in range(4) for h in range(2))
-        assert got == list(range(8 * lane, 8 * lane + 8))
-
-
-def segmented_item(prod, flags_bits):
-    """Phase 2a of csr_stream_kernel for one item: prod[256] products in logical order, flags_bits[256] row-start bits.
-    Returns the segment totals seg[] exactly as the 32 lanes compute them (per-lane closes, segmented scan, stores)."""
-    seg = {}
-    f = [sum(int(flags_bits[8 * t + j]) << j for j in range(8)) for t in range(32)]
-    nf_before = [sum(bin(f[u]).count("1") for u in range(t)) for t in range(32)]
-    acc, head, seen = [0.0] * 32, [0.0] * 32, [0] * 32
-    for t in range(32):
-        a, s = 0.0, 0
-        for j in range(8):
-            if (f[t] >> j) & 1:
-                if s == 0:
-                    head[t] = a
-                else:
-                    seg[nf_before[t] + s] = a
-                a = 0.0
-                s += 1
-            a += prod[8 * t + j]
-        acc[t], seen[t] = a, s
-    has = [f[t] != 0 for t in range(32)]
-    S = acc[:]
-    off = 1
-    while off < 32:
-        new = S[:]
-        for t in range(32):
-            if t >= off and not any(has[t - off + 1:t + 1]):
-                new[t] = S[t - off] + S[t]
-        S = new
-        off <<= 1
-    for t in range(32):
-        if has[t]:
-            seg[nf_before[t]] = (S[t - 1] if t > 0 else 0.0) + head[t]
-    seg[nf_before[31] + seen[31]] = S[31]
-    return seg
-
-
-@pytest.mark.parametrize("kind", ["short", "long", "mixed", "empty_rows", "one_row"])
-def test_segmented_reduction_gives_every_row_its_sum(kind):
-    rng = np.random.default_rng({"short": 1, "long": 2, "mixed": 3, "empty_rows": 4, "one_row": 5}[kind])
-    if kind == "one_row":
-        lens = np.array([700])
-    else:
-        lens = {"short": rng.integers(1, 4, 400), "long": rng.integers(60, 400, 12), "mixed": rng.integers(0, 40, 120),
-                "empty_rows": rng.integers(0, 3, 700) * rng.integers(0, 2, 700)}[kind]
-    rp = np.concatenate([[0], np.cumsum(lens)])
-    nnz, rows = int(rp[-1]), len(lens)
-    prod = rng.integers(-8, 9, size=((nnz + 255) // 256) * 256).astype(float)     # exact in fp64: any summation order agrees
-    prod[nnz:] = 0.0
-    flags = np.zeros(len(prod), bool)
-    for r in range(rows):
-        if rp[r + 1] > rp[r]:
-            flags[rp[r]] = True
-    want = np.array([prod[rp[r]:rp[r + 1]].sum() for r in range(rows)])
-    got = np.zeros(rows)
-    for item in range(len(prod) // 256):
-        s, e = item * 256, min((item + 1) * 256, nnz)
-        if s >= nnz:
-            break
-        seg = segmented_item(prod[s:s + 256], flags[s:s + 256])
-        rA = int(np.searchsorted(rp[1:], s, side="right"))                         # first row with rowPtr[r+1] > s
-        seg0 = 0 if rp[rA] < s else 1
-        seen_rows = 0
-        r = rA
-        while r < rows and rp[r] < e:
-            a, b = max(rp[r], s), min(rp[r + 1], e)
-            if b > a:
-                got[r] += seg[seg0 + seen_rows]                                     # partial sums of a cut row add up across items
-                seen_rows += 1
-            r += 1
-    assert np.array_equal(got, want)
