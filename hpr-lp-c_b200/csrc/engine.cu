@@ -688,6 +688,7 @@ void Engine::alloc_common() {
     };
     tex_y = make_tex(y, m); tex_xhat = make_tex(x_hat, n);
     tex_q = make_tex(wm2, m); tex_atq = make_tex(wn, n);   // power iteration: q and A^T q
+    tex_ybar = make_tex(y_bar, m); tex_xbar = make_tex(x_bar, n); tex_xtmp = make_tex(x_tmp, n);   // check passes
     A.G = pick_lanes(A.mean_len, "HPRLP_LANES_A");
     AT.G = pick_lanes(AT.mean_len, "HPRLP_LANES_AT");
 }
@@ -819,6 +820,11 @@ void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st) {
     HPR_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
     return p;
 }
+void *pool_alloc_raw(size_t bytes, int device, cudaStream_t st) {   // stream-ordered, not zeroed; release with cudaFreeAsync
+    void *p = nullptr;
+    HPR_CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), engine_pool(device), st));
+    return p;
+}
 void pool_free(void *p, cudaStream_t st) {
     if (!p) return;
     static const bool no_pool = getenv("HPRLP_NO_POOL") != nullptr;
@@ -927,7 +933,7 @@ Engine::~Engine() {
     for (auto &kv : graphs_) cudaGraphExecDestroy(kv.second);
     graphs_.clear();
     t[1] = now_seconds();
-    for (cudaTextureObject_t tx : {tex_y, tex_xhat, tex_q, tex_atq})
+    for (cudaTextureObject_t tx : {tex_y, tex_xhat, tex_q, tex_atq, tex_ybar, tex_xbar, tex_xtmp})
         if (tx) cudaDestroyTextureObject(tx);
     if (px) { peer_exchange_destroy(px, coll, stream); px = nullptr; }   // collective: agrees that no peer still uses the buffers
     t[2] = now_seconds();
@@ -1318,7 +1324,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     if (timing) { cudaEventCreate(&te0); cudaEventCreate(&te1); cudaEventRecord(te0, stream); host0 = now_seconds(); }
     auto fill_dual = [&](auto &o) {
         o.y_bar = y_bar; o.c = c; o.z_bar = z_bar; o.x_bar = x_bar; o.x_tmp = x_tmp; o.col_norm = col_norm;
-        o.l = l; o.u = u; o.partials = d_partials;
+        o.l = l; o.u = u; o.tex = tex_ybar; o.partials = d_partials;
     };
     if (dist()) {
         SpmvOp<false> ow; ow.g = y_bar; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
@@ -1339,7 +1345,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     }
     auto fill_primal = [&](auto &o) {
         o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
-        o.y_bar = y_bar; o.y_tmp = y_tmp; o.partials = d_partials;
+        o.y_bar = y_bar; o.y_tmp = y_tmp; o.tex = tex_xbar; o.partials = d_partials;
     };
     {
         ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream);
@@ -1350,7 +1356,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         // restart gap terms <A dx, dy>, |dy|^2 (slots 7, 8) as a second single-product pass.  The two-product variant
         // (ResidualPrimalOp<true>) doubles the shared-memory staging; at 6 CTAs/SM that leaves ~28 KB of L1, i.e. hardly any
         // in-flight gather misses: measured 4.5 ms on C3 against 0.6 ms per single-product pass (same row sums bit for bit).
-        WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
+        WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.tex = tex_xtmp; o.partials = d_partials;
         launch_stream(A, o, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal + 7);
         launches += 2;
@@ -1399,7 +1405,7 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
 // reference compute_weighted_norm, src/main_iterate.cu:486-515
 double Engine::weighted_norm_after_restart() {
     if (dist()) coll->all_gather_inplace(x_tmp, xblock, stream);   // A dx needs every block of dx
-    WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.partials = d_partials;
+    WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.tex = tex_xtmp; o.partials = d_partials;
     launch_stream(A, o, stream);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp + xb0, xb1 - xb0, d_partials);   // |dx|^2 over the owned block

@@ -182,6 +182,7 @@ class Engine {
     void *arena_ = nullptr;         // single device allocation all buffers are carved from
     double *zo_buf = nullptr;       // n doubles for the unscaled z on output
     cudaTextureObject_t tex_y = 0, tex_xhat = 0, tex_q = 0, tex_atq = 0;   // gathered vectors bound as int2 linear textures
+    cudaTextureObject_t tex_ybar = 0, tex_xbar = 0, tex_xtmp = 0;          // ... of the residual / restart-gap passes
 
    private:
     void alloc_common();
@@ -228,6 +229,7 @@ void release_cached_device_memory();
 void warm_device(int device);   // first-solve warm-up: context, modules, cuRAND (errors ignored)
 void *pool_alloc_zeroed(size_t bytes, int device, cudaStream_t st);
 void pool_free(void *p, cudaStream_t st);
+void *pool_alloc_raw(size_t bytes, int device, cudaStream_t st);
 void h2d_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // src may be reused on return; dst is stream-ordered
 void d2h_large(void *dst, const void *src, size_t bytes, cudaStream_t stream);   // returns when the copy is complete
 

@@ -378,6 +378,15 @@ __global__ void build_item_rows_kernel(const RP *rowPtr, int rows, long long nnz
 // ================================================================================================
 // Ops
 // ================================================================================================
+// gather through the TEX pipe when the vector is bound as a linear texture (tex != 0), else ld.global.nc
+__device__ __forceinline__ double gather_tex_or_ldg(cudaTextureObject_t tex, const double *vec, int col) {
+    if (tex) {
+        const int2 t = tex1Dfetch<int2>(tex, col);
+        return __hiloint2double(t.y, t.x);
+    }
+    return __ldg(vec + col);
+}
+
 struct OpBase {
     static constexpr int NV = 1;
     static constexpr bool kMax = false;
@@ -483,13 +492,14 @@ struct YPhaseOp : OpBase {
 template <bool GAP, bool ITER0>
 struct ResidualDualOp : OpBase {
     const double *y_bar, *c, *z_bar, *x_bar, *x_tmp, *col_norm, *l, *u;
+    cudaTextureObject_t tex;   // y_bar as a texture (0: plain loads)
     double *partials;
     double t[5];
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int s = 0; s < 5; ++s) t[s] = 0.0;
     }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(y_bar + col); }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * gather_tex_or_ldg(tex, y_bar, col); }
     __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) {
         const double cj = c[j], zb = z_bar[j], xb = x_bar[j], cn = col_norm[j];
@@ -514,6 +524,7 @@ template <bool GAP>
 struct ResidualPrimalOp : OpBase {
     static constexpr int NV = GAP ? 2 : 1;
     const double *x_bar, *x_tmp, *AL, *AU, *row_norm, *y_obj, *y_bar, *y_tmp;
+    cudaTextureObject_t tex;   // x_bar as a texture (0: plain loads)
     double *partials;
     double t[4];
     __device__ __forceinline__ void init() {
@@ -521,7 +532,7 @@ struct ResidualPrimalOp : OpBase {
         for (int s = 0; s < 4; ++s) t[s] = 0.0;
     }
     __device__ __forceinline__ void elem(double v, int col, double (&o)[NV]) const {
-        o[0] = v * __ldg(x_bar + col);
+        o[0] = v * gather_tex_or_ldg(tex, x_bar, col);
         if (GAP) o[NV - 1] = v * __ldg(x_tmp + col);
     }
     __device__ __forceinline__ void elem_b(double v, int col, double (&o)[NV]) const { elem(v, col, o); }
@@ -539,10 +550,11 @@ struct ResidualPrimalOp : OpBase {
 // src/main_iterate.cu:486-515): slots 0 <A dx, dy>, 1 |dy|^2.
 struct WeightedNormOp : OpBase {
     const double *dx, *dy;
+    cudaTextureObject_t tex;   // dx as a texture (0: plain loads)
     double *partials;
     double t[2];
     __device__ __forceinline__ void init() { t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * __ldg(dx + col); }
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * gather_tex_or_ldg(tex, dx, col); }
     __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
     __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) {
         const double d = dy[i];

@@ -103,17 +103,20 @@ void device_transpose_csr(int rows, int cols, int nnz, const int *d_rowPtr, cons
     int *rowid = nullptr, *idx = nullptr, *keys_out = nullptr, *perm = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    // stream-ordered temporaries from the device memory pool (cached across solves, no synchronous cudaMalloc/cudaFree)
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&rowid), sizeof(int) * (size_t)nnz, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&idx), sizeof(int) * (size_t)nnz, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&keys_out), sizeof(int) * (size_t)nnz, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&perm), sizeof(int) * (size_t)nnz, st));
+    // stream-ordered temporaries from the engines' private memory pool (cached across solves, no synchronous cudaMalloc/cudaFree)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto pool_get = [&](size_t bytes) { return pool_alloc_raw(bytes, dev, st); };
+    rowid = static_cast<int *>(pool_get(sizeof(int) * (size_t)nnz));
+    idx = static_cast<int *>(pool_get(sizeof(int) * (size_t)nnz));
+    keys_out = static_cast<int *>(pool_get(sizeof(int) * (size_t)nnz));
+    perm = static_cast<int *>(pool_get(sizeof(int) * (size_t)nnz));
     const int T = 256;
     nnz_row_ids_kernel<<<(nnz + T - 1) / T, T, 0, st>>>(d_rowPtr, rows, nnz, rowid, idx);
     int bits = 1;
     while (bits < 31 && (1LL << bits) < (long long)cols) ++bits;
     HPR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_col, keys_out, idx, perm, nnz, 0, bits, st));
-    HPR_CUDA_CHECK(cudaMallocAsync(&tmp, std::max<size_t>(tmp_bytes, 16), st));
+    tmp = pool_get(std::max<size_t>(tmp_bytes, 16));
     HPR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_col, keys_out, idx, perm, nnz, 0, bits, st));
     permute_kernel<<<(nnz + T - 1) / T, T, 0, st>>>(perm, rowid, d_val, nnz, d_tcol, d_tval);
     col_ptr_kernel<<<(cols + 1 + T - 1) / T, T, 0, st>>>(keys_out, nnz, cols, d_trp);
