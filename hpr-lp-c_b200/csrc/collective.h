@@ -42,13 +42,16 @@ Collective *make_nccl_collective(NcclComm comm, int nranks, int rank);   // take
 // of ours instead of two NCCL collectives.  Every rank exposes three cudaMalloc'ed buffers to all the others (raw
 // pointers + cudaDeviceEnablePeerAccess inside one process, CUDA IPC handles between processes; the bootstrap runs
 // over the rank's NCCL communicator):
-//   w      npad doubles: the partial A_p^T y_p this rank's SpMV pass writes
+//   w      npad doubles = one receive slot of `xblock` doubles per rank: slot p holds rank p's partial A_p^T y_p restricted
+//          to THIS rank's x-block, stored there by rank p's own SpMV pass (SpmvPushOp: the reduce-scatter is fused into
+//          the pass, its NVLink traffic runs under the pass)
 //   xhat   npad doubles: the full x_hat this rank's fused y-phase gathers from
 //   flags  2 x 16 epochs: A[q] = "rank q's partial w of epoch e is complete", B[q] = "rank q has stored its x_hat
 //          block of epoch e everywhere" -- written remotely by rank q (st.release.sys), polled locally (ld.acquire.sys)
-// fused_exchange_x_kernel (engine.cu): wait A -> for j in the owned x-block: w_j = sum_q w_q[j] over P2P loads in
-// rank order (deterministic), x-update, x_hat_j stored into EVERY rank's xhat over P2P -> last CTA signals B.
-// NVLink traffic per GPU per iteration: 8 n (P-1)/P bytes in (loads) and the same out (stores), overlapped.
+// fused_exchange_x_kernel (engine.cu): wait A -> for j in the owned x-block: w_j = sum over the P local slots in rank
+// order (deterministic), x-update, x_hat_j stored into EVERY rank's xhat over P2P -> last CTA signals B.
+// NVLink traffic per GPU per iteration: 8 n (P-1)/P bytes out under the SpMV pass (partial w) and the same out of the
+// x-update kernel (x_hat); everything is pushed (stores), nothing is pulled.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerExchange {

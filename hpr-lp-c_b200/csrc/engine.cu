@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(kVecThreads) x_update_kernel(const double *w, 
 }
 // ---- the same exchange + x-update as ONE kernel over NVLink peer memory (collective.h, PeerExchange) ------------------
 struct PeerPtrs {
-    const double *w[kMaxPeers];
     double *xhat[kMaxPeers];
     unsigned long long *flags[kMaxPeers];
 };
@@ -221,11 +220,6 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_peer(const double *p) {   // never served from this SM's L1 (peer lines are L1-cacheable)
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
 // Polls a flag of THIS GPU's memory that a peer GPU writes.  Different GPUs run concurrently, so the wait is finite; the
@@ -247,22 +241,18 @@ __global__ void exchange_signal_kernel(PeerPtrs pp, int P, int rank, int slot, u
 __global__ void exchange_wait_kernel(const unsigned long long *flags, int P, int slot, unsigned long long epoch) {
     if ((int)threadIdx.x < P) wait_epoch(flags + slot * kMaxPeers + threadIdx.x, epoch);
 }
-__device__ __forceinline__ double2 ld_peer2(const double *p) {
-    double2 v;
-    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-}
-// reduce-scatter + x-update + all-gather of one HPR iteration for the x-block [j0, j1) this GPU owns:
-//   wait until every rank's partial w_q = A_q^T y_q is complete;  w_j = sum_q w_q[j] (P2P loads, rank order: the result
-//   does not depend on who finishes first);  x-update (same arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY
-//   rank's x_hat buffer (P2P stores);  the last CTA tells every rank that this block of x_hat is in place.
-// PP = number of ranks (compile time: all PP peer loads of an element pair are issued before the first use -- one NVLink
-// round trip per pair instead of PP) or 0 (any rank count, loads one after the other).  16-byte accesses; j0 is even.
+// reduce (of the scattered partials) + x-update + all-gather of one HPR iteration for the x-block [j0, j1) this GPU owns:
+//   wait until every rank's A_q^T y_q pass has delivered its slot (the passes push their rows into `recv`, SpmvPushOp);
+//   w_j = sum over the P local slots in rank order (the result does not depend on who finished first);  x-update (same
+//   arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY rank's x_hat buffer (P2P stores over NVLink);  the last CTA
+//   tells every rank that this block of x_hat is in place.
+// PP = number of ranks (compile time: unrolled) or 0 (any rank count).  16-byte accesses; j0 is even.
 template <bool CHECK, int PP>
-__global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs pp, int P, int rank, unsigned long long epoch, unsigned *done,
-                                                                      double *x, const double *c, const double *l, const double *u,
-                                                                      const double *x0, double *x_bar, double *z_bar, double *x_tmp,
-                                                                      const double *params, const int *kx, int *ky, int j0, int j1) {
+__global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPtrs pp, const double *recv, size_t xblock, int P, int rank,
+                                                                          unsigned long long epoch, unsigned *done, double *x,
+                                                                          const double *c, const double *l, const double *u, const double *x0,
+                                                                          double *x_bar, double *z_bar, double *x_tmp, const double *params,
+                                                                          const int *kx, int *ky, int j0, int j1) {
     if ((int)threadIdx.x < P) wait_epoch(pp.flags[rank] + threadIdx.x, epoch);
     __syncthreads();
     const double sigma = params[0];
@@ -279,15 +269,16 @@ __global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs 
     const int npairs = (j1 - j0) >> 1;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs; t += gridDim.x * blockDim.x) {
         const int j = j0 + 2 * t;
+        const double *rw = recv + 2 * t;   // slot q of this pair at rw + q * xblock
         double2 w = make_double2(0.0, 0.0);
         if (PP > 0) {
             double2 wv[PP > 0 ? PP : 1];
 #pragma unroll
-            for (int q = 0; q < PP; ++q) wv[q] = ld_peer2(pp.w[q] + j);
+            for (int q = 0; q < PP; ++q) wv[q] = __ldcs(reinterpret_cast<const double2 *>(rw + (size_t)q * xblock));
 #pragma unroll
             for (int q = 0; q < PP; ++q) { w.x += wv[q].x; w.y += wv[q].y; }
         } else {
-            for (int q = 0; q < P; ++q) { const double2 v = ld_peer2(pp.w[q] + j); w.x += v.x; w.y += v.y; }
+            for (int q = 0; q < P; ++q) { const double2 v = __ldcs(reinterpret_cast<const double2 *>(rw + (size_t)q * xblock)); w.x += v.x; w.y += v.y; }
         }
         const double2 xi = *reinterpret_cast<const double2 *>(x + j), cj = *reinterpret_cast<const double2 *>(c + j);
         const double2 lj = *reinterpret_cast<const double2 *>(l + j), uj = *reinterpret_cast<const double2 *>(u + j);
@@ -306,7 +297,7 @@ __global__ void __launch_bounds__(kVecThreads) fused_exchange_x_kernel(PeerPtrs 
     if (((j1 - j0) & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd block length: the last entry
         const int j = j1 - 1;
         double w = 0.0;
-        for (int q = 0; q < P; ++q) w += ld_peer(pp.w[q] + j);
+        for (int q = 0; q < P; ++q) w += recv[(size_t)q * xblock + (j - j0)];
         double xn, xh;
         update(j, w, x[j], c[j], l[j], u[j], x0[j], xn, xh);
         x[j] = xn;
@@ -373,7 +364,7 @@ static CsrView<int> view_of(const DevCsr &M) {
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
     v.head_part = M.head_part; v.tail_part = M.tail_part; v.ticket = M.ticket;
-    v.carry_in = nullptr; v.carry_out = nullptr;
+    v.carry_in = nullptr; v.carry_out = nullptr; v.chunk_offset = 0;
     return v;
 }
 
@@ -661,9 +652,16 @@ void Engine::alloc_common() {
     if (dist()) px = peer_exchange_create(coll, device, npad, stream);   // collective: every rank, same point of the setup
     x = dalloc<double>(nv); x0 = dalloc<double>(nv); x_bar = dalloc<double>(nv);
     z_bar = dalloc<double>(nv); x_tmp = dalloc<double>(nv);
-    // the two exchanged vectors live in peer-visible (cudaMalloc + IPC) memory when the NVLink exchange is on
+    // x_hat lives in peer-visible (cudaMalloc + IPC) memory when the NVLink exchange is on: the peers store their blocks into it
     x_hat = px ? px->xhat[rank] : dalloc<double>(nv);
-    wn = px ? px->w[rank] : dalloc<double>(nv);
+    if (px) {   // the push pass of this rank starts at the x-block after its own (partial_ATy_pass)
+        const size_t j = std::min<size_t>((size_t)n, xblock * (size_t)((rank + 1) % nranks));
+        int p = 0;
+        HPR_CUDA_CHECK(cudaMemcpyAsync(&p, AT.rowPtr + j, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        AT.push_chunk0 = (int)(((long long)p / kChunk) % std::max(AT.n_items, 1));
+    }
+    wn = dalloc<double>(nv);
     y = dalloc<double>(m); y0 = dalloc<double>(m); y_bar = dalloc<double>(m); y_obj = dalloc<double>(m);
     y_tmp = dalloc<double>(m); wm = dalloc<double>(m); wm2 = dalloc<double>(m);
     row_norm = dalloc<double>(m); col_norm = dalloc<double>(n);
@@ -1232,15 +1230,15 @@ void Engine::launch_y_phase(bool check) {
 // wn holds this rank's partial A_p^T y_p.  On return x (owned block) is updated and x_hat is complete on every rank.
 void Engine::exchange_x(bool check) {
     const int gx = vec_grid(xb1 - xb0);
-    if (px) {
+    if (push_mode()) {   // the partials are already in (or on their way to) the owners' receive slots: partial_ATy_pass()
         PeerPtrs pp;
-        for (int q = 0; q < kMaxPeers; ++q) { pp.w[q] = px->w[q]; pp.xhat[q] = px->xhat[q]; pp.flags[q] = px->flags[q]; }
+        for (int q = 0; q < kMaxPeers; ++q) { pp.xhat[q] = px->xhat[q]; pp.flags[q] = px->flags[q]; }
         const unsigned long long e = ++px->epoch;
-        exchange_signal_kernel<<<1, 32, 0, stream>>>(pp, nranks, rank, 0, e);
+        exchange_signal_kernel<<<1, 32, 0, stream>>>(pp, nranks, rank, 0, e);   // "my pass has delivered everywhere"
         const int gp = vec_grid((xb1 - xb0 + 1) / 2);   // one element pair per thread and pass
         auto launch = [&](auto kernel, bool chk) {
-            kernel<<<gp, kVecThreads, 0, stream>>>(pp, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr, chk ? z_bar : nullptr,
-                                                   chk ? x_tmp : nullptr, d_params, d_k, d_k + 1, xb0, xb1);
+            kernel<<<gp, kVecThreads, 0, stream>>>(pp, px->w[rank], xblock, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr,
+                                                   chk ? z_bar : nullptr, chk ? x_tmp : nullptr, d_params, d_k, d_k + 1, xb0, xb1);
         };
         if (check) launch(fused_exchange_x_kernel<true, 0>, true);   // check iterations are rare: one generic instantiation
         else switch (nranks) {
@@ -1264,12 +1262,26 @@ void Engine::exchange_x(bool check) {
     launches += 1;
 }
 
+// The x-side pass of a row-partitioned iteration: w_p = A_p^T y_p.  NCCL transport: into wn (reduce-scattered afterwards).
+// Peer-memory transport: every row result goes straight to the receive slot of the column's owner (SpmvPushOp), each rank
+// starting at the x-block after its own so that the owners are targeted by one peer at a time.
+void Engine::partial_ATy_pass() {
+    if (!push_mode()) { launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream); return; }
+    SpmvPushOp o;
+    o.g = y; o.tex = tex_y; o.xblock = (int)xblock;
+    for (int q = 0; q < kMaxPeers; ++q)
+        o.slot[q] = q < nranks ? px->w[q] + ((long long)rank - q) * (long long)xblock : nullptr;
+    CsrView<int> v = view_of(AT);
+    v.chunk_offset = AT.push_chunk0;
+    dispatch_hot(v, AT.G, o, stream);
+}
+
 void Engine::launch_iteration(bool check) {
     if (dist()) {
         // Row-partitioned iteration: partial w_p = A_p^T y_p over the local rows, reduce-scatter so that this
         // GPU holds (A^T y) on ITS x-block, x-update on that block only, all-gather of the x_hat blocks, then the fused
         // y-phase on the local rows of A with the full x_hat.
-        launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream);
+        partial_ATy_pass();
         exchange_x(check);
         launch_y_phase(check);
         launches += 2;
@@ -1499,11 +1511,11 @@ double Engine::time_phase_ms(int which, int reps) {
     HPR_CUDA_CHECK(cudaEventCreate(&e1));
     auto one = [&]() {
         if (which == 0) launch_x_phase(false);
-        else if (which == 2) launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream);   // row-partitioned x-side pass
+        else if (which == 2) partial_ATy_pass();   // row-partitioned x-side pass
         else if (which == 3)   // row-partitioned x-update on the owned block (from whatever wn holds)
             x_update_kernel<false><<<vec_grid(xb1 - xb0), kVecThreads, 0, stream>>>(wn, x, x_hat, c, l, u, x0, nullptr, nullptr, nullptr, d_params, d_k, d_k + 1, xb0, xb1);
         else if (which == 4) {   // the exchange of one iteration, as the loop issues it
-            if (coll && px) exchange_x(false);   // peer-memory path: the exchange IS the fused x-update kernel
+            if (coll && push_mode()) exchange_x(false);   // peer-memory path: the exchange IS the fused x-update kernel
             else if (coll) { coll->reduce_scatter_inplace(wn, xblock, stream); coll->all_gather_inplace(x_hat, xblock, stream); }
         } else launch_y_phase(false);
         launches++;

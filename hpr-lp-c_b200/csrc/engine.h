@@ -44,6 +44,7 @@ struct DevCsr {
     int n_items = 0;
     PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries (all-ones = empty)
     unsigned long long *ticket = nullptr;   // chunk tickets handed out by csr_stream_kernel over all launches (kernels.cuh)
+    int push_chunk0 = 0;    // first chunk of the row-partitioned push pass of this rank (kernels.cuh, CsrView::chunk_offset)
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;
     int max_len = 0;
@@ -151,6 +152,8 @@ class Engine {
     Collective *coll = nullptr;
     PeerExchange *px = nullptr;    // NVLink peer-memory exchange (collective.h); null: NCCL reduce-scatter + all-gather
     void exchange_x(bool check);   // reduce-scatter + x-update on the owned block + all-gather, by either transport
+    void partial_ATy_pass();       // w_p = A_p^T y_p into wn, or (peer exchange) pushed into the owners' receive slots
+    bool push_mode() const { return px != nullptr && AT.bands.empty(); }
     int nranks = 1, rank = 0, m_global = 0, row0 = 0;
     int xb0 = 0, xb1 = 0;          // owned columns
     size_t xblock = 0, npad = 0;   // exchange block (multiple of 64 entries), padded n-vector length

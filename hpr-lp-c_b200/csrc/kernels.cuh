@@ -78,6 +78,10 @@ struct CsrView {
     PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
     unsigned long long *ticket;   // chunk tickets handed out so far over ALL launches on this matrix (never reset: every
                                   // launch has exactly n_items CTAs and each takes one, so chunk = ticket % n_items)
+    int chunk_offset;             // chunks are handed out starting at this one (cyclically); 0 except for the row-partitioned
+                                  // push pass, where every rank starts at a different x-block so that no GPU is the target
+                                  // of all peers at once.  Only the row cut at the wrap-around boundary then waits for an
+                                  // item that starts LATER (the very last one): a bounded wait, not a deadlock.
     // Column-banded matrices (engine.cu, build_bands): a pass over the matrix is one launch per band; every band but the
     // last stores its row sums (+ those of the bands before it) in carry_out instead of running the epilogue, the last
     // band adds carry_in to its own row sums first.  Both null for an ordinary matrix.  Single-product ops only.
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     // The chunk this CTA works on comes from a ticket: chunks are handed out in the order CTAs START, so every item to
     // the left of ours belongs to a CTA that is already running (or done) -- the look-back below cannot wait for a CTA
     // that was never scheduled, whatever order the hardware dispatches blockIdx in.
-    if (threadIdx.x == 0) chunk_s = (unsigned)(atomicAdd(M.ticket, 1ULL) % (unsigned long long)gridDim.x);
+    if (threadIdx.x == 0) chunk_s = (unsigned)((atomicAdd(M.ticket, 1ULL) + (unsigned long long)M.chunk_offset) % (unsigned long long)gridDim.x);
     if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
     const int chunk = (int)chunk_s;
@@ -591,6 +595,19 @@ struct SpmvOp : OpBase {
     __device__ __forceinline__ void finish(double *scratch, int block) {
         if (DOTS) block_reduce_store<2>(t, partials, scratch, block);
     }
+};
+
+// Row-partitioned x-side pass with the reduce-scatter fused in (collective.h, PeerExchange): w_p = A_p^T y_p, and row j
+// of the result is stored straight into the receive slot that the OWNER of column j keeps for this rank -- a peer store
+// over NVLink for remote owners -- so the transfer runs under the pass instead of after it.
+struct SpmvPushOp : OpBase {
+    const double *g;
+    cudaTextureObject_t tex;   // g as an int2 linear texture (0: plain loads)
+    double *slot[16];          // slot[q][j] = where row j goes if rank q owns it (= recv buffer of q + (rank - q) * xblock)
+    int xblock;
+    __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * gather_tex_or_ldg(tex, g, col); }
+    __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { elem(v, col, o); }
+    __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const { slot[j / xblock][j] = acc[0]; }
 };
 
 // Row statistic for Ruiz (sqrt max|a|) and Pock-Chambolle (sqrt sum|a|) scaling
