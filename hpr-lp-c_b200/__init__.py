@@ -20,7 +20,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = ROOT / "lib" / "libhprlp.so"
+LIB_PATH = Path(os.environ["HPRLP_LIB"]) if os.environ.get("HPRLP_LIB") else ROOT / "lib" / "libhprlp.so"   # HPRLP_LIB: tuning variants (tools/build_variants.sh)
 REF_LIB_PATH = ROOT / "oracle" / "_ref" / "libhprlp_ref.so"
 ORACLE_LIB_PATH = ROOT / "oracle" / "liboracle.so"
 SYNTH_LIB_PATH = ROOT / "tools" / "libsynth.so"

@@ -42,7 +42,16 @@ namespace {
 constexpr int kGS = 32;            // instances per group = lanes per warp
 constexpr int kBThreads = 256;     // 8 warps per CTA
 constexpr int kBWarps = kBThreads / 32;
-constexpr int kRowsPerCta = 32;    // 4 rows per warp
+#ifndef HPR_B_ROWS
+#define HPR_B_ROWS 32
+#endif
+#ifndef HPR_B_MINB
+#define HPR_B_MINB 6
+#endif
+#ifndef HPR_B_PIPE
+#define HPR_B_PIPE 0
+#endif
+constexpr int kRowsPerCta = HPR_B_ROWS;    // rows per CTA (8 warps): the software pipeline of the row loop needs a few rows per warp to fill
 constexpr double kInfReplacement = 1.0e100;   // reference src/batched_solver.cu:17
 
 struct BView {
@@ -79,8 +88,13 @@ __device__ __forceinline__ void st_once(double *p, double v) { __stcs(p, v); }
 // independent gathers + FMAs per lane and A is streamed once per kNG groups.  Built and measured in round 2: it does NOT
 // pay on B200 (see BatchedSolver::ngx) -- the passes are limited by the bytes the gathers pull through the L2, which
 // register blocking does not reduce, and kNG slabs thrash the L2 -- so kNG = 1 is the default.
+// The row loop is software-pipelined (r2): a row costs a CHAIN of memory round trips -- row extent -> (col, val) ->
+// gathers -> epilogue operands -- and ncu showed the r1 kernel waiting on that chain with nothing saturated (L2 34-39 %,
+// L1TEX 49-59 %, DRAM 32-46 % of peak).  Here the epilogue operands of the row (Op::pre) and the NEXT row's extent are
+// requested before the gathers, and the next row's first 32 (col, val) pairs under them: one exposed round trip per row
+// (the gathers) instead of four.
 template <class Op>
-__global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 4 : 6)) batched_rows_kernel(BView M, Op op, int G) {
+__global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 4 : HPR_B_MINB)) batched_rows_kernel(BView M, Op op, int G) {
     constexpr int NG = Op::kNG;
     __shared__ double red[kBWarps][kMaxSlots][kGS];
     const int g0 = blockIdx.y * NG;
@@ -89,15 +103,34 @@ __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 
     const unsigned long long keep = make_keep_policy();
     const int row0 = blockIdx.x * kRowsPerCta;
     const int row1 = min(M.rows, row0 + kRowsPerCta);
-    for (int r = row0 + warp; r < row1; r += kBWarps) {
-        const int p0 = M.rowPtr[r], p1 = M.rowPtr[r + 1];
+    int r = row0 + warp;
+    int p0 = 0, p1 = 0, c = 0;
+    double v = 0.0;
+    if (r < row1) {
+        p0 = M.rowPtr[r]; p1 = M.rowPtr[r + 1];
+        if (p0 + lane < p1) { c = __ldg(M.col + p0 + lane); v = __ldg(M.val + p0 + lane); }
+    }
+    while (r < row1) {
+        const int rn = r + kBWarps;
+        int np0 = 0, np1 = 0, nc = 0;
+        double nv = 0.0;
+#if HPR_B_PIPE
+        if (rn < row1) { np0 = M.rowPtr[rn]; np1 = M.rowPtr[rn + 1]; }   // next row's extent: in flight under this row's gathers
+#endif
+#if HPR_B_PIPE == 1
+        typename Op::Pre pre[NG];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) pre[q] = op.pre(r, q);              // epilogue operands of this row: likewise
+#endif
         double acc[NG];
 #pragma unroll
         for (int q = 0; q < NG; ++q) acc[q] = 0.0;
         for (int k0 = p0; k0 < p1; k0 += 32) {
-            const int kk = k0 + lane;
-            const int c = (kk < p1) ? __ldg(M.col + kk) : 0;
-            const double v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
+            if (k0 != p0) {                                               // rows longer than 32 nonzeros: the later chunks
+                const int kk = k0 + lane;
+                c = (kk < p1) ? __ldg(M.col + kk) : 0;
+                v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
+            }
             const int cnt = min(32, p1 - k0);
 #pragma unroll 4
             for (int t = 0; t < cnt; ++t) {
@@ -106,9 +139,25 @@ __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 
 #pragma unroll
                 for (int q = 0; q < NG; ++q) op.accum(vv, cc, q, acc[q], keep);
             }
+#if HPR_B_PIPE == 1
+            if (k0 == p0 && np0 + lane < np1) { nc = __ldg(M.col + np0 + lane); nv = __ldg(M.val + np0 + lane); }
+#endif
         }
+#if HPR_B_PIPE == 1
+        if (p1 <= p0 && np0 + lane < np1) { nc = __ldg(M.col + np0 + lane); nv = __ldg(M.val + np0 + lane); }   // (empty row)
+#else
+#if HPR_B_PIPE == 0
+        if (rn < row1) { np0 = M.rowPtr[rn]; np1 = M.rowPtr[rn + 1]; }
+#endif
+        // after the gathers have been issued: the next row's first 32 (col, val) pairs and this row's epilogue operands
+        if (np0 + lane < np1) { nc = __ldg(M.col + np0 + lane); nv = __ldg(M.val + np0 + lane); }
+        typename Op::Pre pre[NG];
 #pragma unroll
-        for (int q = 0; q < NG; ++q) op.row(r, q, acc[q]);
+        for (int q = 0; q < NG; ++q) pre[q] = op.pre(r, q);
+#endif
+#pragma unroll
+        for (int q = 0; q < NG; ++q) op.row(r, q, acc[q], pre[q]);
+        r = rn; p0 = np0; p1 = np1; c = nc; v = nv;
     }
     op.finish(red, warp, lane);
 }
@@ -163,6 +212,8 @@ struct BOpBase {
         acc = fma(v, ld_keep(gp[q] + (size_t)col * kGS, keep), acc);
     }
     __device__ __forceinline__ void finish(double (*)[kMaxSlots][kGS], int, int) {}
+    struct Pre {};   // epilogue operands requested before the gathers (ops that have none)
+    __device__ __forceinline__ Pre pre(int, int) const { return Pre{}; }
 };
 
 // x-phase (reference update_x_z_{normal,check}_batched_kernel, src/batched_solver.cu:122-178)
@@ -192,12 +243,20 @@ struct BXOp : BOpBase<NG> {
             if (Base::valid[q] && blockIdx.x == 0 && threadIdx.x < 32) ky[inst] = k;
         }
     }
-    __device__ __forceinline__ void row(int r, int q, double acc) const {
+    struct Pre { double xi, c, l, u, x0; };
+    __device__ __forceinline__ Pre pre(int r, int q) const {
+        Pre p{0.0, 0.0, 0.0, 0.0, 0.0};
+        if (!on[q]) return p;
+        const size_t t = Base::obase[q] + (size_t)r * kGS;
+        p.xi = ld_once(X + t); p.c = ld_once(C + t); p.l = ld_once(L + t); p.u = ld_once(U + t); p.x0 = ld_once(lastX + t);
+        return p;
+    }
+    __device__ __forceinline__ void row(int r, int q, double acc, const Pre &p) const {
         if (!on[q]) return;
         const size_t t = Base::obase[q] + (size_t)r * kGS;
-        const double xi = ld_once(X + t);
-        const double zt = fma(sig[q], acc - ld_once(C + t), xi);
-        const double xb = fmin(fmax(zt, ld_once(L + t)), ld_once(U + t));
+        const double xi = p.xi;
+        const double zt = fma(sig[q], acc - p.c, xi);
+        const double xb = fmin(fmax(zt, p.l), p.u);
         const double xh = 2.0 * xb - xi;
         if (CHECK) {
             st_once(DX + t, xb - xh);
@@ -205,7 +264,7 @@ struct BXOp : BOpBase<NG> {
             st_once(X_bar + t, xb);
         }
         X_hat[t] = xh;   // gathered by the y-phase that follows: normal priority
-        st_once(X + t, fma(f2[q], xh, f1[q] * ld_once(lastX + t)));
+        st_once(X + t, fma(f2[q], xh, f1[q] * p.x0));
     }
 };
 
@@ -238,12 +297,20 @@ struct BYOp : BOpBase<NG> {
             if (on[q] && blockIdx.x == 0 && threadIdx.x < 32) kx[inst] = k + 1;
         }
     }
-    __device__ __forceinline__ void row(int r, int q, double acc) const {
+    struct Pre { double yi, al, au, y0; };
+    __device__ __forceinline__ Pre pre(int r, int q) const {
+        Pre p{0.0, 0.0, 0.0, 0.0};
+        if (!on[q]) return p;
+        const size_t t = Base::obase[q] + (size_t)r * kGS;
+        p.yi = ld_once(Y + t); p.al = ld_once(AL + t); p.au = ld_once(AU + t); p.y0 = ld_once(lastY + t);
+        return p;
+    }
+    __device__ __forceinline__ void row(int r, int q, double acc, const Pre &p) const {
         if (!on[q]) return;
         const size_t t = Base::obase[q] + (size_t)r * kGS;
-        const double yi = ld_once(Y + t);
+        const double yi = p.yi;
         const double v = fma(-fact1[q], yi, acc);
-        const double d = fmax(ld_once(AL + t) - v, fmin(ld_once(AU + t) - v, 0.0));
+        const double d = fmax(p.al - v, fmin(p.au - v, 0.0));
         const double yb = d / fact1[q];
         const double yh = 2.0 * yb - yi;
         if (CHECK) {
@@ -251,7 +318,7 @@ struct BYOp : BOpBase<NG> {
             st_once(Y_bar + t, yb);
             st_once(Y_obj + t, v + d);
         }
-        Y[t] = fma(f2[q], yh, f1[q] * ld_once(lastY + t));   // gathered by the next x-phase: normal priority
+        Y[t] = fma(f2[q], yh, f1[q] * p.y0);   // gathered by the next x-phase: normal priority
     }
 };
 
@@ -263,7 +330,7 @@ struct BResDualOp : BOpBase<1> {
     double *partials;
     double t[4];
     __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(Y_bar, g0, lane, G); t[0] = t[1] = t[2] = t[3] = 0.0; }
-    __device__ __forceinline__ void row(int j, int, double acc) {
+    __device__ __forceinline__ void row(int j, int, double acc, const Pre &) {
         const size_t i = obase[0] + (size_t)j * kGS;
         const double cj = C[i], zb = Z_bar[i], xb = X_bar[i], cn = col_norm[j];
         const double rd = (cj - acc - zb) * cn;
@@ -288,7 +355,7 @@ struct BResPrimalOp : BOpBase<1> {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(X_bar, g0, lane, G); t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void row(int r, int, double ax) {
+    __device__ __forceinline__ void row(int r, int, double ax, const Pre &) {
         const size_t i = obase[0] + (size_t)r * kGS;
         const double rp = row_norm[r] * fmax(fmin(AU[i] - ax, 0.0), AL[i] - ax);
         t[0] += rp * rp;
@@ -305,7 +372,7 @@ struct BWeightedOp : BOpBase<1> {
     double *partials;
     double t[2];
     __device__ __forceinline__ void init(int g0, int lane, int G) { init_base(DX, g0, lane, G); t[0] = t[1] = 0.0; }
-    __device__ __forceinline__ void row(int r, int, double acc) {
+    __device__ __forceinline__ void row(int r, int, double acc, const Pre &) {
         const double dy = DY[obase[0] + (size_t)r * kGS];
         t[0] += acc * dy;
         t[1] += dy * dy;
