@@ -381,12 +381,15 @@ class HprLib:
         B = C_.shape[0] if _B is None else _B
         oc = _f64(obj_constants) if obj_constants is not None else None
         args = (model, B, _dp(C_), _dp(AL), _dp(AU), _dp(l), _dp(u), _dp(oc), C.byref(param) if param is not None else None)
+        import time as _time
+        t0 = _time.perf_counter()
         if _layout is not None:
             res = self.lib.hprlp_b200_solve_batched_layout(*args, int(_layout))
         else:
             res = self.lib.solve_batched(*args) if n_gpus is None else self.lib.hprlp_b200_solve_batched_multi(*args, int(n_gpus))
+        call_seconds = _time.perf_counter() - t0      # the C-ABI call alone: host arrays in, malloc'ed host arrays out
         out = dict(m=res.m, n=res.n, batch_size=res.batch_size, time=res.time, setup_time=res.setup_time,
-                   solve_time=res.solve_time, power_time=res.power_time)
+                   solve_time=res.solve_time, power_time=res.power_time, call_seconds=call_seconds)
         if res.status:
             raw = C.string_at(res.status, 64 * B)
             out["status"] = [raw[64 * k:64 * k + 64].split(b"\0")[0].decode() for k in range(B)]
