@@ -364,8 +364,15 @@ static CsrView<int> view_of(const DevCsr &M) {
     v.rows = M.rows; v.nnz = M.nnz; v.rowPtr = M.rowPtr; v.col = M.col; v.val = M.val;
     v.item_row = M.item_row; v.n_items = M.n_items;
     v.head_part = M.head_part; v.tail_part = M.tail_part; v.ticket = M.ticket;
+    v.issued_host = const_cast<unsigned long long *>(&M.tickets_issued);
     v.carry_in = nullptr; v.carry_out = nullptr; v.chunk_offset = 0;
     return v;
+}
+
+// tickets after which the (32-bit) chunk counter of a matrix is re-zeroed between launches; HPRLP_TICKET_WRAP: tests
+static unsigned long long ticket_wrap() {
+    static const unsigned long long w = getenv("HPRLP_TICKET_WRAP") ? strtoull(getenv("HPRLP_TICKET_WRAP"), nullptr, 10) : 0xC0000000ull;
+    return w;
 }
 
 template <class Op, int G>
@@ -379,6 +386,16 @@ static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
         if (const char *e = getenv("HPRLP_CARVEOUT"))   // tuning hook: shared-memory carve-out in percent
             HPR_CUDA_CHECK(cudaFuncSetAttribute(csr_stream_kernel<Op, G, int>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
         configured.fetch_or(1u << dev);
+    }
+    // ticket counter: a multiple of n_items between launches; zeroed here (stream-ordered) long before 2^32
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {   // (captured launches are accounted for per replay in run_normal)
+        if (*v.issued_host + (unsigned long long)v.n_items > ticket_wrap()) {
+            HPR_CUDA_CHECK(cudaMemsetAsync(v.ticket, 0, sizeof(unsigned), st));
+            *v.issued_host = 0;
+        }
+        *v.issued_host += (unsigned long long)v.n_items;
     }
     csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
 }
@@ -551,7 +568,7 @@ static void alloc_matrix(DevCsr &M, int rows, int cols, long long nnz) {
     M.item_row = dalloc<int>(witems + 1);
     M.head_part = dalloc<PartSlot>(witems * 2);   // all-ones = "not published" (set in finish_matrix); consumers re-arm what they read
     M.tail_part = dalloc<PartSlot>(witems * 2);
-    M.ticket = dalloc<unsigned long long>(1);
+    M.ticket = dalloc<unsigned>(1);
 }
 static void free_matrix(DevCsr &M) {
     dfree(M.rowPtr); dfree(M.col); dfree(M.val); dfree(M.item_row);
@@ -580,7 +597,8 @@ void Engine::finish_matrix(DevCsr &M) {
     const size_t part_bytes = sizeof(PartSlot) * (size_t)M.n_items * kWarps * 2;
     HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0xFF, part_bytes, stream));   // every packet "not published"
     HPR_CUDA_CHECK(cudaMemsetAsync(M.tail_part, 0xFF, part_bytes, stream));
-    HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned long long), stream));
+    HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned), stream));
+    M.tickets_issued = 0;
     M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
 }
 
@@ -612,7 +630,7 @@ void Engine::build_bands(DevCsr &M) {
         o_item[b] = total; total += up((wit + 1) * sizeof(int));
         o_head[b] = total; total += up(wit * 2 * sizeof(PartSlot));
         o_tail[b] = total; total += up(wit * 2 * sizeof(PartSlot));
-        o_tick[b] = total; total += up(sizeof(unsigned long long));
+        o_tick[b] = total; total += up(sizeof(unsigned));
     }
     const size_t o_carry = total; total += up((size_t)M.rows * sizeof(double));
     const size_t o_ptrs = total;  total += up(sizeof(void *) * 2 * nb);
@@ -630,7 +648,7 @@ void Engine::build_bands(DevCsr &M) {
         Bd.item_row = reinterpret_cast<int *>(store + o_item[b]);
         Bd.head_part = reinterpret_cast<PartSlot *>(store + o_head[b]);
         Bd.tail_part = reinterpret_cast<PartSlot *>(store + o_tail[b]);
-        Bd.ticket = reinterpret_cast<unsigned long long *>(store + o_tick[b]);
+        Bd.ticket = reinterpret_cast<unsigned *>(store + o_tick[b]);
         ptrs[b] = Bd.col; ptrs[nb + b] = Bd.val;
     }
     HPR_CUDA_CHECK(cudaMemcpyAsync(store + o_ptrs, ptrs.data(), sizeof(void *) * 2 * nb, cudaMemcpyHostToDevice, stream));
@@ -1319,6 +1337,13 @@ void Engine::run_normal(int count) {
                 HPR_CUDA_CHECK(cudaGraphInstantiate(&ge, g, nullptr, nullptr, 0));
                 cudaGraphDestroy(g);
                 it = graphs_.emplace(len, ge).first;
+            }
+            for (DevCsr *M : {&A, &AT}) {   // one launch per matrix and iteration inside the graph: keep the ticket bookkeeping exact
+                if (M->tickets_issued + (unsigned long long)len * M->n_items > ticket_wrap()) {
+                    HPR_CUDA_CHECK(cudaMemsetAsync(M->ticket, 0, sizeof(unsigned), stream));
+                    M->tickets_issued = 0;
+                }
+                M->tickets_issued += (unsigned long long)len * M->n_items;
             }
             HPR_CUDA_CHECK(cudaGraphLaunch(it->second, stream));
             launches += 2LL * len;

@@ -43,7 +43,8 @@ struct DevCsr {
     int *item_row = nullptr;
     int n_items = 0;
     PartSlot *head_part = nullptr, *tail_part = nullptr;   // partial sums of rows cut by item boundaries (all-ones = empty)
-    unsigned long long *ticket = nullptr;   // chunk tickets handed out by csr_stream_kernel over all launches (kernels.cuh)
+    unsigned *ticket = nullptr;             // chunk tickets handed out by csr_stream_kernel since the last zeroing (kernels.cuh)
+    unsigned long long tickets_issued = 0;  // host count of the same: the counter is re-zeroed between launches before it can wrap
     int push_chunk0 = 0;    // first chunk of the row-partitioned push pass of this rank (kernels.cuh, CsrView::chunk_offset)
     int G = 1;              // lanes per row in phase 2, from the mean row length
     double mean_len = 0.0;

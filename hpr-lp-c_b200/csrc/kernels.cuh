@@ -76,8 +76,12 @@ struct CsrView {
     int n_items;          // CTAs in the grid
     PartSlot *head_part;  // [items * 2] partial of the row entering the item from the left (and leaving it to the right)
     PartSlot *tail_part;  // [items * 2] partial of the row that starts in the item and leaves it to the right
-    unsigned long long *ticket;   // chunk tickets handed out so far over ALL launches on this matrix (never reset: every
-                                  // launch has exactly n_items CTAs and each takes one, so chunk = ticket % n_items)
+    unsigned *ticket;             // chunk tickets handed out since the counter was last zeroed.  Every launch has exactly
+                                  // n_items CTAs and each takes one, so chunk = ticket % n_items without any reset between
+                                  // launches; the host zeroes the counter (stream-ordered, between launches) long before it
+                                  // can wrap (launch_one, engine.cu).  32-bit on purpose: the 64-bit remainder is a ~100
+                                  // instruction routine that one thread would execute while the CTA waits at the barrier.
+    unsigned long long *issued_host;   // HOST bookkeeping for that (never dereferenced on the device)
     int chunk_offset;             // chunks are handed out starting at this one (cyclically); 0 except for the row-partitioned
                                   // push pass, where every rank starts at a different x-block so that no GPU is the target
                                   // of all peers at once.  Only the row cut at the wrap-around boundary then waits for an
@@ -187,12 +191,16 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     // The chunk this CTA works on comes from a ticket: chunks are handed out in the order CTAs START, so every item to
     // the left of ours belongs to a CTA that is already running (or done) -- the look-back below cannot wait for a CTA
     // that was never scheduled, whatever order the hardware dispatches blockIdx in.
-    if (threadIdx.x == 0) chunk_s = (unsigned)((atomicAdd(M.ticket, 1ULL) + (unsigned long long)M.chunk_offset) % (unsigned long long)gridDim.x);
+#ifdef HPR_STATIC_CHUNKS   // measurement only (tools/build_variants.sh): chunk = blockIdx, i.e. r1's dispatch-order assumption
+    if (threadIdx.x == 0) chunk_s = blockIdx.x;
+#else
+    if (threadIdx.x == 0) chunk_s = (atomicAdd(M.ticket, 1u) % gridDim.x + (unsigned)M.chunk_offset) % gridDim.x;
+#endif
     if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
+    op.init();         // its loads (sigma, Halpern counter) do not depend on the chunk: in flight under the ticket's round trip
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
     const int chunk = (int)chunk_s;
 
-    op.init();
     auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
         if (M.carry_in) t[0] += M.carry_in[r];
         if (M.carry_out) M.carry_out[r] = t[0];

@@ -111,3 +111,33 @@ def test_time_limit_is_honoured_between_checks(pkg, engine):
     assert r["status"] == "TIME_LIMIT"
     assert 0.25 <= r["time"] < 0.6, r["time"]          # not tens of thousands of iterations later
     assert wall < 3.0
+
+
+def test_ticket_counter_is_rezeroed_before_it_can_wrap(pkg, engine):
+    """The chunk ticket of csr_stream_kernel is a 32-bit counter that only ever grows by n_items per launch; the host
+    re-zeroes it between launches long before 2^32.  HPRLP_TICKET_WRAP makes that happen every few launches (direct
+    launches and the CUDA-graph path of small LPs): same bits as without.  (The variable is read once per process, so
+    the forced run happens in a child process.)"""
+    import json, os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import json, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        import __graft_entry__ as g
+        pkg = g.load_package(); eng = pkg.load_engine()
+        out = {}
+        for name, (kind, m, n, nnz, it) in dict(direct=("powerlaw", 20000, 50000, 3000000, 300), graph=("uniform", 300, 900, 3600, 700)).items():
+            lp = pkg.synth_lp(kind, m, n, nnz)
+            p = pkg.Parameters.default(use_presolve=False, max_iter=it, stop_tol=1e-30)
+            model = eng.create_model(lp)
+            r = eng.solve(model, p, main=True)
+            eng.free_model(model)
+            out[name] = [float(np.sum(r["x"])), float(np.sum(r["y"])), float(np.sum(np.abs(r["z"]))), r["iter"]]
+        print("RESULT " + json.dumps(out))
+    ''') % str(pkg.ROOT)
+    def run(env_extra):
+        env = dict(os.environ, **env_extra)
+        pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert pr.returncode == 0, pr.stderr[-2000:]
+        return json.loads([ln for ln in pr.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
+    assert run({"HPRLP_TICKET_WRAP": "3000"}) == run({})
