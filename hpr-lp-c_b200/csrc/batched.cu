@@ -51,6 +51,11 @@ constexpr int kBWarps = kBThreads / 32;
 #ifndef HPR_B_PIPE
 #define HPR_B_PIPE 0
 #endif
+#ifndef HPR_B_UNROLL
+#define HPR_B_UNROLL 4
+#endif
+#define HPR_PRAGMA_(x) _Pragma(#x)
+#define HPR_UNROLL_(n) HPR_PRAGMA_(unroll n)
 constexpr int kRowsPerCta = HPR_B_ROWS;    // rows per CTA (8 warps): the software pipeline of the row loop needs a few rows per warp to fill
 constexpr double kInfReplacement = 1.0e100;   // reference src/batched_solver.cu:17
 
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 
                 v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
             }
             const int cnt = min(32, p1 - k0);
-#pragma unroll 4
+HPR_UNROLL_(HPR_B_UNROLL)
             for (int t = 0; t < cnt; ++t) {
                 const int cc = __shfl_sync(0xffffffffu, c, t);
                 const double vv = __shfl_sync(0xffffffffu, v, t);
