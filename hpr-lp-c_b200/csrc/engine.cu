@@ -247,7 +247,9 @@ __global__ void exchange_wait_kernel(const unsigned long long *flags, int P, int
 //   arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY rank's x_hat buffer (P2P stores over NVLink);  the last CTA
 //   tells every rank that this block of x_hat is in place.
 // PP = number of ranks (compile time: unrolled) or 0 (any rank count).  16-byte accesses; j0 is even.
-template <bool CHECK, int PP>
+// PLAIN: no x-update -- the sum itself is what every rank receives (an all-reduce of the pushed partials: the A^T q of the
+// power iteration, gathered afterwards from the x_hat buffer, which is free then).
+template <bool CHECK, int PP, bool PLAIN = false>
 __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPtrs pp, const double *recv, size_t xblock, int P, int rank,
                                                                           unsigned long long epoch, unsigned *done, double *x,
                                                                           const double *c, const double *l, const double *u, const double *x0,
@@ -255,11 +257,12 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
                                                                           const int *kx, int *ky, int j0, int j1) {
     if ((int)threadIdx.x < P) wait_epoch(pp.flags[rank] + threadIdx.x, epoch);
     __syncthreads();
-    const double sigma = params[0];
-    const int k = *kx;
+    const double sigma = PLAIN ? 1.0 : params[0];
+    const int k = PLAIN ? 0 : *kx;
     const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
+    if (!PLAIN && blockIdx.x == 0 && threadIdx.x == 0) *ky = k;
     auto update = [&](int j, double w, double xi, double cj, double lj, double uj, double x0j, double &xn, double &xh) {
+        if (PLAIN) { xh = w; xn = 0.0; return; }
         const double zt = fma(sigma, w - cj, xi);
         const double xb = fmin(uj, fmax(lj, zt));
         xh = 2.0 * xb - xi;
@@ -280,13 +283,16 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
         } else {
             for (int q = 0; q < P; ++q) { const double2 v = __ldcs(reinterpret_cast<const double2 *>(rw + (size_t)q * xblock)); w.x += v.x; w.y += v.y; }
         }
-        const double2 xi = *reinterpret_cast<const double2 *>(x + j), cj = *reinterpret_cast<const double2 *>(c + j);
-        const double2 lj = *reinterpret_cast<const double2 *>(l + j), uj = *reinterpret_cast<const double2 *>(u + j);
-        const double2 xa = *reinterpret_cast<const double2 *>(x0 + j);
+        double2 xi = make_double2(0.0, 0.0), cj = xi, lj = xi, uj = xi, xa = xi;
+        if (!PLAIN) {
+            xi = *reinterpret_cast<const double2 *>(x + j); cj = *reinterpret_cast<const double2 *>(c + j);
+            lj = *reinterpret_cast<const double2 *>(l + j); uj = *reinterpret_cast<const double2 *>(u + j);
+            xa = *reinterpret_cast<const double2 *>(x0 + j);
+        }
         double2 xn, xh;
         update(j, w.x, xi.x, cj.x, lj.x, uj.x, xa.x, xn.x, xh.x);
         update(j + 1, w.y, xi.y, cj.y, lj.y, uj.y, xa.y, xn.y, xh.y);
-        *reinterpret_cast<double2 *>(x + j) = xn;
+        if (!PLAIN) *reinterpret_cast<double2 *>(x + j) = xn;
         if (PP > 0) {
 #pragma unroll
             for (int q = 0; q < PP; ++q) *reinterpret_cast<double2 *>(pp.xhat[q] + j) = xh;
@@ -299,8 +305,8 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
         double w = 0.0;
         for (int q = 0; q < P; ++q) w += recv[(size_t)q * xblock + (j - j0)];
         double xn, xh;
-        update(j, w, x[j], c[j], l[j], u[j], x0[j], xn, xh);
-        x[j] = xn;
+        if (PLAIN) update(j, w, 0.0, 0.0, 0.0, 0.0, 0.0, xn, xh);
+        else { update(j, w, x[j], c[j], l[j], u[j], x0[j], xn, xh); x[j] = xn; }
         for (int q = 0; q < P; ++q) pp.xhat[q][j] = xh;
     }
     __threadfence_system();   // this thread's peer stores are performed before the CTA is counted as done
@@ -1171,9 +1177,16 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     int it;
     for (it = 1; it <= max_iter; ++it) {
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
-        launch_spmv_hot<false>(AT, q, tex_q, atq, nullptr, nullptr, stream);
-        allreduce(atq, n);   // A^T q = sum over row blocks
-        launch_spmv_hot<true>(A, atq, tex_atq, z, q, d_partials, stream);
+        if (dist() && push_mode()) {   // A^T q = sum over row blocks: rows pushed to their owners, summed there, sent to everyone's x_hat
+            partial_ATy_pass(q, tex_q);
+            exchange_x(false, true);
+            launch_spmv_hot<true>(A, x_hat, tex_xhat, z, q, d_partials, stream);
+            launches += 3;
+        } else {
+            launch_spmv_hot<false>(AT, q, tex_q, atq, nullptr, nullptr, stream);
+            allreduce(atq, n);   // A^T q = sum over row blocks
+            launch_spmv_hot<true>(A, atq, tex_atq, z, q, d_partials, stream);
+        }
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
         allreduce(d_scal, 2);
         launches += 4;
@@ -1246,7 +1259,7 @@ void Engine::launch_y_phase(bool check) {
     else          { if (check) go(YPhaseOp<true, false>()); else go(YPhaseOp<false, false>()); }
 }
 // wn holds this rank's partial A_p^T y_p.  On return x (owned block) is updated and x_hat is complete on every rank.
-void Engine::exchange_x(bool check) {
+void Engine::exchange_x(bool check, bool plain) {
     const int gx = vec_grid(xb1 - xb0);
     if (push_mode()) {   // the partials are already in (or on their way to) the owners' receive slots: partial_ATy_pass()
         PeerPtrs pp;
@@ -1258,7 +1271,8 @@ void Engine::exchange_x(bool check) {
             kernel<<<gp, kVecThreads, 0, stream>>>(pp, px->w[rank], xblock, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr,
                                                    chk ? z_bar : nullptr, chk ? x_tmp : nullptr, d_params, d_k, d_k + 1, xb0, xb1);
         };
-        if (check) launch(fused_exchange_x_kernel<true, 0>, true);   // check iterations are rare: one generic instantiation
+        if (plain) launch(fused_exchange_x_kernel<false, 0, true>, false);   // sum of the pushed partials to every rank's x_hat
+        else if (check) launch(fused_exchange_x_kernel<true, 0>, true);   // check iterations are rare: one generic instantiation
         else switch (nranks) {
             case 2: launch(fused_exchange_x_kernel<false, 2>, false); break;
             case 3: launch(fused_exchange_x_kernel<false, 3>, false); break;
@@ -1283,10 +1297,11 @@ void Engine::exchange_x(bool check) {
 // The x-side pass of a row-partitioned iteration: w_p = A_p^T y_p.  NCCL transport: into wn (reduce-scattered afterwards).
 // Peer-memory transport: every row result goes straight to the receive slot of the column's owner (SpmvPushOp), each rank
 // starting at the x-block after its own so that the owners are targeted by one peer at a time.
-void Engine::partial_ATy_pass() {
-    if (!push_mode()) { launch_spmv_hot<false>(AT, y, tex_y, wn, nullptr, nullptr, stream); return; }
+void Engine::partial_ATy_pass(const double *g, cudaTextureObject_t tex) {
+    if (!g) { g = y; tex = tex_y; }
+    if (!push_mode()) { launch_spmv_hot<false>(AT, g, tex, wn, nullptr, nullptr, stream); return; }
     SpmvPushOp o;
-    o.g = y; o.tex = tex_y; o.xblock = (int)xblock;
+    o.g = g; o.tex = tex; o.xblock = (int)xblock;
     for (int q = 0; q < kMaxPeers; ++q)
         o.slot[q] = q < nranks ? px->w[q] + ((long long)rank - q) * (long long)xblock : nullptr;
     CsrView<int> v = view_of(AT);

@@ -152,8 +152,8 @@ class Engine {
     // coll == nullptr: single GPU.
     Collective *coll = nullptr;
     PeerExchange *px = nullptr;    // NVLink peer-memory exchange (collective.h); null: NCCL reduce-scatter + all-gather
-    void exchange_x(bool check);   // reduce-scatter + x-update on the owned block + all-gather, by either transport
-    void partial_ATy_pass();       // w_p = A_p^T y_p into wn, or (peer exchange) pushed into the owners' receive slots
+    void exchange_x(bool check, bool plain = false);   // reduce-scatter + x-update on the owned block + all-gather, by either transport
+    void partial_ATy_pass(const double *g = nullptr, cudaTextureObject_t tex = 0);   // w_p = A_p^T g_p (g = y by default) into wn, or (peer exchange) pushed into the owners' receive slots
     bool push_mode() const { return px != nullptr && AT.bands.empty(); }
     int nranks = 1, rank = 0, m_global = 0, row0 = 0;
     int xb0 = 0, xb1 = 0;          // owned columns
