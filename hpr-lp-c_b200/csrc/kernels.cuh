@@ -52,6 +52,9 @@ constexpr int kWarps = kThreads / 32;
 #ifndef HPR_TEX_GATHER
 #define HPR_TEX_GATHER 1
 #endif
+#ifndef HPR_BULK_STREAM
+#define HPR_BULK_STREAM 0   // 1: the col/val item is brought into shared memory by two cp.async.bulk (TMA engine) copies per warp
+#endif
 constexpr int kLaneNnz = HPR_LANE_NNZ;          // nonzeros per lane per item
 constexpr int kRoundNnz = HPR_ROUND_NNZ;        // nonzeros per lane per load round (loads in flight)
 constexpr int kWarpChunk = 32 * kLaneNnz;       // nonzeros per warp item
@@ -134,6 +137,32 @@ __device__ __forceinline__ double part_consume_cta(PartSlot *p) {
 __device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
 __device__ __forceinline__ int2 ld_stream(const int2 *p) { return __ldcs(p); }
 
+// ---- bulk-async (TMA engine) copy of a contiguous global range into shared memory, completion on an mbarrier -----------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    // make the initialised barrier visible to the async proxy (the TMA engine completes transactions on it); CTA scope on
+    // purpose: fence.mbarrier_init.release.cluster compiles to CCTL.IVALL, i.e. an L1 flush per warp item
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // Block-wide deterministic sum of NS per-thread accumulators; thread 0 writes them to
 // out[blockIdx.x * kMaxSlots + s].  The caller's final_reduce_kernel adds the per-CTA values
 // in block order, so every reduction is run-to-run reproducible.
@@ -173,7 +202,8 @@ __device__ __forceinline__ double combine(double a, double b) { return MAX ? fma
 // ------------------------------------------------------------------------------------------------
 template <class Op>
 constexpr size_t stream_smem_bytes() {
-    return sizeof(double) * ((size_t)kWarps * Op::NV * kWarpChunk + (size_t)kMaxSlots * kWarps);
+    return sizeof(double) * ((size_t)kWarps * Op::NV * kWarpChunk + (size_t)kMaxSlots * kWarps) +
+           (HPR_BULK_STREAM ? (size_t)kWarps * (sizeof(int) * kWarpChunk + 16) : 0);   // + column-index stage and one mbarrier per warp
 }
 
 template <class Op, int G, typename RP>
@@ -223,6 +253,33 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     }
 
     // ---- phase 1: stream nonzeros, gather, multiply (kRoundNnz loads in flight per lane) -----------
+#if HPR_BULK_STREAM
+    if constexpr (NV == 1) {
+        // The warp's 3 KB of (col, val) arrive by two bulk-async copies issued by one lane (TMA engine, no LSU wavefronts for the
+        // stream); the values land in the product slice itself and are overwritten by the products.
+        int *col_stage = reinterpret_cast<int *>(red_scratch + kMaxSlots * kWarps) + warp * kWarpChunk;
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<int *>(red_scratch + kMaxSlots * kWarps) + kWarps * kWarpChunk) + 2 * warp;
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, kWarpChunk * 12);
+            bulk_g2s(prod, M.val + s, kWarpChunk * 8, bar);
+            bulk_g2s(col_stage, M.col + s, kWarpChunk * 4, bar);
+        }
+        mbar_wait(bar, 0);
+        const int2 *c2 = reinterpret_cast<const int2 *>(col_stage);
+#pragma unroll
+        for (int u = 0; u < kLaneNnz / 2; ++u) {
+            const int t = u * 32 + lane;
+            const int2 cc = c2[t];
+            const double2 vv = *reinterpret_cast<const double2 *>(prod + 2 * t);
+            double o0[NV], o1[NV];
+            op.elem(vv.x, cc.x, o0);
+            op.elem_b(vv.y, cc.y, o1);
+            *reinterpret_cast<double2 *>(prod + 2 * t) = make_double2(o0[0], o1[0]);
+        }
+    } else
+#endif
     {
         const double2 *v2 = reinterpret_cast<const double2 *>(M.val + s);
         const int2 *c2 = reinterpret_cast<const int2 *>(M.col + s);
