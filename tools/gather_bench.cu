@@ -18,7 +18,11 @@
 //   spmv_tex   index + value stream + TEX gather + FMA (the whole phase-1 of the product kernel, no reduction)
 //   tmaT       index stream, T of the 8 gathers per lane through cp.async.bulk (16 B, TMA unit -> shared memory,
 //              bypasses the L1 tag stage), the rest through TEX
+//   dsmemC     index stream + gathers from DISTRIBUTED SHARED MEMORY: the vector (V <= C * slice) is spread over the shared
+//              memory of a C-CTA thread-block cluster (C = 8 portable, 16 non-portable), one 1024-thread CTA per SM, every
+//              gather an ld.shared::cluster to the CTA that holds the entry (only vectors <= ~1.6 MB fit)
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -155,6 +159,39 @@ gather_tma_kernel(const int *__restrict__ col, const double *__restrict__ g, cud
     if (acc == 123.456) out[blockIdx.x * kThreads + threadIdx.x] = acc;
 }
 
+namespace cg = cooperative_groups;
+// slice = 2^SHIFT doubles of the vector per CTA of the cluster
+template <int SHIFT>
+__global__ void __launch_bounds__(1024, 1)
+gather_dsmem_kernel(const int *__restrict__ col, const double *__restrict__ g, int V, long long n_items, double *out) {
+    extern __shared__ __align__(16) double vec[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned r = cluster.block_rank();
+    constexpr int slice = 1 << SHIFT;
+    for (int i = threadIdx.x; i < slice; i += blockDim.x) {
+        const long long gi = (long long)r * slice + i;
+        vec[i] = gi < V ? g[gi] : 0.0;
+    }
+    cluster.sync();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warps_total = (long long)gridDim.x * 32;
+    double acc = 0.0;
+    for (long long item = (long long)blockIdx.x * 32 + warp; item < n_items; item += warps_total) {
+        const int2 *c2 = reinterpret_cast<const int2 *>(col + item * kWarpChunk);
+        int2 cc[kLaneNnz / 2];
+#pragma unroll
+        for (int u = 0; u < kLaneNnz / 2; ++u) cc[u] = __ldcs(c2 + u * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < kLaneNnz / 2; ++u) {
+            const double *a = cluster.map_shared_rank(vec + (cc[u].x & (slice - 1)), (unsigned)(cc[u].x >> SHIFT));
+            const double *b = cluster.map_shared_rank(vec + (cc[u].y & (slice - 1)), (unsigned)(cc[u].y >> SHIFT));
+            acc += *a + *b;
+        }
+    }
+    cluster.sync();   // no CTA may retire while a peer can still read its shared memory
+    if (acc == 123.456) out[blockIdx.x * 1024 + threadIdx.x] = acc;
+}
+
 struct Result { std::string mode; int V; double ms, gps; };
 
 int main(int argc, char **argv) {
@@ -203,6 +240,23 @@ int main(int argc, char **argv) {
         CK(cudaFuncSetAttribute(gather_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         run("tma" #T, [&] { gather_tma_kernel<T><<<grid, kThreads, sm>>>(col, g, tex, V, out); }); } while (0)
         RUNT(1); RUNT(2); RUNT(4); RUNT(8);
+        if (V <= 131072) {   // the vector fits a cluster's distributed shared memory
+            auto dsmem = [&](const char *name, auto kernel, int cluster_size, int shift) {
+                const size_t sm = sizeof(double) << shift;
+                CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                if (cluster_size > 8) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+                const int n_clusters = prop.multiProcessorCount / cluster_size;
+                cfg.gridDim = dim3(n_clusters * cluster_size); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = sm;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                const long long n_items = nnz / kWarpChunk;
+                run(name, [&] { CK(cudaLaunchKernelEx(&cfg, kernel, (const int *)col, (const double *)g, V, n_items, out)); });
+            };
+            dsmem("dsmem8", gather_dsmem_kernel<14>, 8, 14);     // 8 x 16384 doubles (128 KB per CTA)
+            dsmem("dsmem16", gather_dsmem_kernel<13>, 16, 13);   // 16 x 8192 doubles (64 KB per CTA)
+        }
         CK(cudaDestroyTextureObject(tex));
         CK(cudaFree(g));
     }
