@@ -141,3 +141,16 @@ def test_ticket_counter_is_rezeroed_before_it_can_wrap(pkg, engine):
         assert pr.returncode == 0, pr.stderr[-2000:]
         return json.loads([ln for ln in pr.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     assert run({"HPRLP_TICKET_WRAP": "3000"}) == run({})
+
+
+def test_warmup_then_solve(pkg, engine):
+    """hprlp_b200_warmup starts the context / cuRAND warm-up on a background thread; the next solve joins it."""
+    engine.lib.hprlp_b200_warmup.argtypes = [C.c_int]
+    engine.lib.hprlp_b200_warmup.restype = None
+    engine.lib.hprlp_b200_warmup(0)
+    engine.lib.hprlp_b200_warmup(0)          # idempotent
+    lp = pkg.synth_lp("uniform", 300, 900, 3600)
+    model = engine.create_model(lp)
+    r = engine.solve(model, pkg.Parameters.default(use_presolve=False, stop_tol=1e-6), main=True)
+    engine.free_model(model)
+    assert r["status"] == "OPTIMAL"
