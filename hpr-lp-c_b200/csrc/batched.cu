@@ -54,6 +54,9 @@ constexpr int kBWarps = kBThreads / 32;
 #ifndef HPR_B_UNROLL
 #define HPR_B_UNROLL 4
 #endif
+#ifndef HPR_B_ROWS2
+#define HPR_B_ROWS2 0   // 1: a warp works on two rows at once (twice the independent loads in flight per warp)
+#endif
 #define HPR_PRAGMA_(x) _Pragma(#x)
 #define HPR_UNROLL_(n) HPR_PRAGMA_(unroll n)
 constexpr int kRowsPerCta = HPR_B_ROWS;    // rows per CTA (8 warps): the software pipeline of the row loop needs a few rows per warp to fill
@@ -108,6 +111,39 @@ __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 
     const unsigned long long keep = make_keep_policy();
     const int row0 = blockIdx.x * kRowsPerCta;
     const int row1 = min(M.rows, row0 + kRowsPerCta);
+#if HPR_B_ROWS2
+    if constexpr (NG == 1) {
+        for (int rA = row0 + warp; rA < row1; rA += 2 * kBWarps) {
+            const int rB = rA + kBWarps;
+            const bool hasB = rB < row1;
+            const int a0 = M.rowPtr[rA], a1 = M.rowPtr[rA + 1];
+            const int b0 = hasB ? M.rowPtr[rB] : 0, b1 = hasB ? M.rowPtr[rB + 1] : 0;
+            double accA = 0.0, accB = 0.0;
+            const int lenA = a1 - a0, lenB = b1 - b0;
+            for (int k0 = 0; k0 < lenA || k0 < lenB; k0 += 32) {
+                const int ka = a0 + k0 + lane, kb = b0 + k0 + lane;
+                const int cA = (ka < a1) ? __ldg(M.col + ka) : 0, cB = (kb < b1) ? __ldg(M.col + kb) : 0;
+                const double vA = (ka < a1) ? __ldg(M.val + ka) : 0.0, vB = (kb < b1) ? __ldg(M.val + kb) : 0.0;
+                const int cntA = max(0, min(32, lenA - k0)), cntB = max(0, min(32, lenB - k0));
+                const int cnt = max(cntA, cntB);
+HPR_UNROLL_(HPR_B_UNROLL)
+                for (int t = 0; t < cnt; ++t) {
+                    const int ccA = __shfl_sync(0xffffffffu, cA, t), ccB = __shfl_sync(0xffffffffu, cB, t);
+                    const double vvA = __shfl_sync(0xffffffffu, vA, t), vvB = __shfl_sync(0xffffffffu, vB, t);
+                    if (t < cntA) op.accum(vvA, ccA, 0, accA, keep);
+                    if (t < cntB) op.accum(vvB, ccB, 0, accB, keep);
+                }
+            }
+            const typename Op::Pre preA = op.pre(rA, 0);
+            typename Op::Pre preB{};
+            if (hasB) preB = op.pre(rB, 0);
+            op.row(rA, 0, accA, preA);
+            if (hasB) op.row(rB, 0, accB, preB);
+        }
+        op.finish(red, warp, lane);
+        return;
+    }
+#endif
     int r = row0 + warp;
     int p0 = 0, p1 = 0, c = 0;
     double v = 0.0;
