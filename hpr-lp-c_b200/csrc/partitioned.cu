@@ -92,6 +92,8 @@ HPRLP_results solve_rank(const LP_info_cpu *model, const std::vector<int> &b, in
                          const HPRLP_parameters &param, bool quiet, hprlp_b200_info *info) {
     HPRLP_parameters pp = param;
     pp.device_number = device;
+    if (const char *e = std::getenv("HPRLP_TEST_FAIL_RANK"))   // tests: this rank fails before its first collective
+        if (std::atoi(e) == p) throw std::runtime_error("injected failure (HPRLP_TEST_FAIL_RANK)");
     Engine eng;
     eng.set_partition(coll, model->m, b[p]);
     SolveHooks hooks;

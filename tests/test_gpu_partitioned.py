@@ -120,3 +120,25 @@ def test_device_generated_partitioned_solve_matches_host_lp(pkg, engine, gpus):
     assert abs(dev["primal_obj"] - host["primal_obj"]) <= 1e-8 * (1 + abs(host["primal_obj"]))
     for k in "xyz":
         assert np.max(np.abs(dev[k] - host[k])) <= 1e-6 * max(1.0, np.max(np.abs(host[k]))), k
+
+
+@pytest.mark.parametrize("transport", ["local", "nccl"])
+def test_a_failing_rank_does_not_hang_its_peers(pkg, engine, transport, monkeypatch):
+    """if one rank throws, the others used to block forever in the next collective.  Now the failing rank
+    aborts every endpoint (ncclCommAbort / poisoned host barrier): the call returns "ERROR" promptly and the library stays
+    usable.  HPRLP_TEST_FAIL_RANK makes rank 1 fail before its first collective while rank 0 is already waiting in one."""
+    import time
+    if transport == "nccl" and _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    lp = pkg.synth_lp("uniform", 3000, 9000, 90000)
+    p = pkg.Parameters.default(use_presolve=False, stop_tol=1e-6)
+    model = engine.create_model(lp)
+    monkeypatch.setenv("HPRLP_TEST_FAIL_RANK", "1")
+    t0 = time.perf_counter()
+    bad = engine.solve_partitioned(model, p, n_gpus=2, local=(transport == "local"))
+    assert bad["status"] == "ERROR" and bad["x"] is None
+    assert time.perf_counter() - t0 < 60
+    monkeypatch.delenv("HPRLP_TEST_FAIL_RANK")
+    ok = engine.solve_partitioned(model, p, n_gpus=2, local=(transport == "local"))
+    engine.free_model(model)
+    assert ok["status"] == "OPTIMAL"
