@@ -194,6 +194,14 @@ PeerExchange *peer_exchange_create(Collective *coll, int device, size_t npad, cu
     std::unique_ptr<PeerExchange> px(new PeerExchange);
     px->P = P; px->rank = rank; px->device = device; px->npad = npad;
     double *dbuf = nullptr;   // bootstrap all-gather buffer
+    auto release_all = [&]() {   // local teardown of whatever exists so far (error paths; nobody else uses the buffers yet)
+        for (int q = 0; q < P; ++q)
+            if (px->ipc_opened[q]) { cudaIpcCloseMemHandle(px->w[q]); cudaIpcCloseMemHandle(px->xhat[q]); cudaIpcCloseMemHandle(px->flags[q]); }
+        cudaFree(px->w[rank]); cudaFree(px->xhat[rank]); cudaFree(px->flags[rank]); cudaFree(px->done);
+        cudaFree(dbuf);
+        cudaGetLastError();
+    };
+    try {
     check_cuda(cudaMalloc(&dbuf, sizeof(double) * kRecDoubles * P), "peer exchange bootstrap");
     PeerRecord mine{};
     mine.pid = (long long)getpid();
@@ -254,19 +262,17 @@ PeerExchange *peer_exchange_create(Collective *coll, int device, size_t npad, cu
         }
     }
     const bool all_ok = all_ranks_ok(coll, ok, dbuf, st);
-    cudaFree(dbuf);
     if (!all_ok) {
         if (rank == 0) std::fprintf(stderr, "[hprlp] peer-memory exchange unavailable (no P2P / IPC mapping): using NCCL reduce-scatter + all-gather\n");
-        PeerExchange *raw = px.release();
-        // nobody uses the buffers: plain local teardown (the vote above was the barrier)
-        for (int q = 0; q < P; ++q)
-            if (raw->ipc_opened[q]) { cudaIpcCloseMemHandle(raw->w[q]); cudaIpcCloseMemHandle(raw->xhat[q]); cudaIpcCloseMemHandle(raw->flags[q]); }
-        cudaFree(raw->w[rank]); cudaFree(raw->xhat[rank]); cudaFree(raw->flags[rank]); cudaFree(raw->done);
-        delete raw;
-        cudaGetLastError();
+        release_all();   // nobody uses the buffers: plain local teardown (the vote above was the barrier)
         return nullptr;
     }
+    cudaFree(dbuf);
     return px.release();
+    } catch (...) {   // a CUDA call or a collective failed (e.g. a peer rank died and the communicator was aborted)
+        release_all();
+        throw;
+    }
 }
 
 void peer_exchange_destroy(PeerExchange *px, Collective *coll, cudaStream_t st) {
