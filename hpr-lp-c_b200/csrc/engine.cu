@@ -247,9 +247,12 @@ __global__ void exchange_wait_kernel(const unsigned long long *flags, int P, int
 //   arithmetic as XPhaseOp::row);  x_hat_j stored into EVERY rank's x_hat buffer (P2P stores over NVLink);  the last CTA
 //   tells every rank that this block of x_hat is in place.
 // PP = number of ranks (compile time: unrolled) or 0 (any rank count).  16-byte accesses; j0 is even.
-// PLAIN: no x-update -- the sum itself is what every rank receives (an all-reduce of the pushed partials: the A^T q of the
-// power iteration, gathered afterwards from the x_hat buffer, which is free then).
-template <bool CHECK, int PP, bool PLAIN = false>
+// MODE 0: the x-update above.  The other modes reuse the kernel's wait / push / signal frame for the remaining exchanges of
+// the partitioned mode (the x_hat buffers are free scratch whenever they run):
+//   1  sum of the slots -> every rank's x_hat           (all-reduce of pushed partials: A^T q of the power iteration)
+//   2  sum of the slots -> my own x_hat block only      (reduce-scatter alone: (A^T y_bar) on the owned block, dual residual)
+//   3  src block [j0, j1) -> every rank's x_hat         (all-gather alone: x_bar / x_bar - x_hat for the primal residual passes)
+template <bool CHECK, int PP, int MODE = 0>
 __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPtrs pp, const double *recv, size_t xblock, int P, int rank,
                                                                           unsigned long long epoch, unsigned *done, double *x,
                                                                           const double *c, const double *l, const double *u, const double *x0,
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
                                                                           const int *kx, int *ky, int j0, int j1) {
     if ((int)threadIdx.x < P) wait_epoch(pp.flags[rank] + threadIdx.x, epoch);
     __syncthreads();
+    constexpr bool PLAIN = MODE != 0;
     const double sigma = PLAIN ? 1.0 : params[0];
     const int k = PLAIN ? 0 : *kx;
     const double f1 = 1.0 / (k + 2.0), f2 = 1.0 - f1;
@@ -274,7 +278,9 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
         const int j = j0 + 2 * t;
         const double *rw = recv + 2 * t;   // slot q of this pair at rw + q * xblock
         double2 w = make_double2(0.0, 0.0);
-        if (PP > 0) {
+        if (MODE == 3) {
+            w = *reinterpret_cast<const double2 *>(recv + 2 * t);   // recv = source vector at j0
+        } else if (PP > 0) {
             double2 wv[PP > 0 ? PP : 1];
 #pragma unroll
             for (int q = 0; q < PP; ++q) wv[q] = __ldcs(reinterpret_cast<const double2 *>(rw + (size_t)q * xblock));
@@ -293,7 +299,9 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
         update(j, w.x, xi.x, cj.x, lj.x, uj.x, xa.x, xn.x, xh.x);
         update(j + 1, w.y, xi.y, cj.y, lj.y, uj.y, xa.y, xn.y, xh.y);
         if (!PLAIN) *reinterpret_cast<double2 *>(x + j) = xn;
-        if (PP > 0) {
+        if (MODE == 2) {
+            *reinterpret_cast<double2 *>(pp.xhat[rank] + j) = xh;
+        } else if (PP > 0) {
 #pragma unroll
             for (int q = 0; q < PP; ++q) *reinterpret_cast<double2 *>(pp.xhat[q] + j) = xh;
         } else {
@@ -303,12 +311,15 @@ __global__ void __launch_bounds__(kVecThreads, 4) fused_exchange_x_kernel(PeerPt
     if (((j1 - j0) & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd block length: the last entry
         const int j = j1 - 1;
         double w = 0.0;
-        for (int q = 0; q < P; ++q) w += recv[(size_t)q * xblock + (j - j0)];
+        if (MODE == 3) w = recv[j - j0];
+        else for (int q = 0; q < P; ++q) w += recv[(size_t)q * xblock + (j - j0)];
         double xn, xh;
         if (PLAIN) update(j, w, 0.0, 0.0, 0.0, 0.0, 0.0, xn, xh);
         else { update(j, w, x[j], c[j], l[j], u[j], x0[j], xn, xh); x[j] = xn; }
-        for (int q = 0; q < P; ++q) pp.xhat[q][j] = xh;
+        if (MODE == 2) pp.xhat[rank][j] = xh;
+        else for (int q = 0; q < P; ++q) pp.xhat[q][j] = xh;
     }
+    if (MODE == 2) return;    // nothing was stored to a peer: nobody waits for this rank
     __threadfence_system();   // this thread's peer stores are performed before the CTA is counted as done
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1179,7 +1190,7 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
         if (dist() && push_mode()) {   // A^T q = sum over row blocks: rows pushed to their owners, summed there, sent to everyone's x_hat
             partial_ATy_pass(q, tex_q);
-            exchange_x(false, true);
+            exchange_x(false, 1);
             launch_spmv_hot<true>(A, x_hat, tex_xhat, z, q, d_partials, stream);
             launches += 3;
         } else {
@@ -1259,7 +1270,7 @@ void Engine::launch_y_phase(bool check) {
     else          { if (check) go(YPhaseOp<true, false>()); else go(YPhaseOp<false, false>()); }
 }
 // wn holds this rank's partial A_p^T y_p.  On return x (owned block) is updated and x_hat is complete on every rank.
-void Engine::exchange_x(bool check, bool plain) {
+void Engine::exchange_x(bool check, int mode, const double *src) {
     const int gx = vec_grid(xb1 - xb0);
     if (push_mode()) {   // the partials are already in (or on their way to) the owners' receive slots: partial_ATy_pass()
         PeerPtrs pp;
@@ -1268,10 +1279,12 @@ void Engine::exchange_x(bool check, bool plain) {
         exchange_signal_kernel<<<1, 32, 0, stream>>>(pp, nranks, rank, 0, e);   // "my pass has delivered everywhere"
         const int gp = vec_grid((xb1 - xb0 + 1) / 2);   // one element pair per thread and pass
         auto launch = [&](auto kernel, bool chk) {
-            kernel<<<gp, kVecThreads, 0, stream>>>(pp, px->w[rank], xblock, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr,
+            kernel<<<gp, kVecThreads, 0, stream>>>(pp, mode == 3 ? src + xb0 : px->w[rank], xblock, nranks, rank, e, px->done, x, c, l, u, x0, chk ? x_bar : nullptr,
                                                    chk ? z_bar : nullptr, chk ? x_tmp : nullptr, d_params, d_k, d_k + 1, xb0, xb1);
         };
-        if (plain) launch(fused_exchange_x_kernel<false, 0, true>, false);   // sum of the pushed partials to every rank's x_hat
+        if (mode == 1) launch(fused_exchange_x_kernel<false, 0, 1>, false);        // sum of the pushed partials to every rank's x_hat
+        else if (mode == 2) launch(fused_exchange_x_kernel<false, 0, 2>, false);   // ... to my own x_hat block
+        else if (mode == 3) launch(fused_exchange_x_kernel<false, 0, 3>, false);   // src block to every rank's x_hat
         else if (check) launch(fused_exchange_x_kernel<true, 0>, true);   // check iterations are rare: one generic instantiation
         else switch (nranks) {
             case 2: launch(fused_exchange_x_kernel<false, 2>, false); break;
@@ -1283,7 +1296,7 @@ void Engine::exchange_x(bool check, bool plain) {
             case 8: launch(fused_exchange_x_kernel<false, 8>, false); break;
             default: launch(fused_exchange_x_kernel<false, 0>, false); break;
         }
-        exchange_wait_kernel<<<1, 32, 0, stream>>>(px->flags[rank], nranks, 1, e);
+        if (mode != 2) exchange_wait_kernel<<<1, 32, 0, stream>>>(px->flags[rank], nranks, 1, e);
         launches += 3;
         return;
     }
@@ -1378,17 +1391,32 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         o.y_bar = y_bar; o.c = c; o.z_bar = z_bar; o.x_bar = x_bar; o.x_tmp = x_tmp; o.col_norm = col_norm;
         o.l = l; o.u = u; o.tex = tex_ybar; o.partials = d_partials;
     };
+    const bool push = dist() && push_mode();
+    const double *xbar_g = x_bar, *xtmp_g = x_tmp;           // what the primal / gap passes gather from
+    cudaTextureObject_t tex_xbar_g = tex_xbar, tex_xtmp_g = tex_xtmp;
     if (dist()) {
-        SpmvOp<false> ow; ow.g = y_bar; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
-        launch_stream(AT, ow, stream);
-        coll->reduce_scatter_inplace(wn, xblock, stream);
         const int gx = vec_grid(xb1 - xb0);
-        if (iter == 0) residual_dual_kernel<false, true><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
-        else if (compute_gap) residual_dual_kernel<true, false><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
-        else residual_dual_kernel<false, false><<<gx, kVecThreads, 0, stream>>>(wn, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        const double *w = wn;
+        if (push) {   // (A^T y_bar) on the owned block: rows pushed to their owners, summed into my x_hat block (free scratch here)
+            partial_ATy_pass(y_bar, tex_ybar);
+            exchange_x(false, 2);
+            w = x_hat;
+        } else {
+            SpmvOp<false> ow; ow.g = y_bar; ow.tex = 0; ow.out = wn; ow.q = nullptr; ow.partials = nullptr;
+            launch_stream(AT, ow, stream);
+            coll->reduce_scatter_inplace(wn, xblock, stream);
+        }
+        if (iter == 0) residual_dual_kernel<false, true><<<gx, kVecThreads, 0, stream>>>(w, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        else if (compute_gap) residual_dual_kernel<true, false><<<gx, kVecThreads, 0, stream>>>(w, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
+        else residual_dual_kernel<false, false><<<gx, kVecThreads, 0, stream>>>(w, c, z_bar, x_bar, x_tmp, col_norm, l, u, xb0, xb1, d_partials);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, gx, 5, d_scal);   // sums over the owned x-block: all-reduced below
-        coll->all_gather_inplace(x_bar, xblock, stream);                          // the primal pass gathers the full x_bar
-        if (compute_gap) coll->all_gather_inplace(x_tmp, xblock, stream);
+        if (push) {   // the primal pass gathers the full x_bar: every rank stores its block into everyone's x_hat
+            exchange_x(false, 3, x_bar);
+            xbar_g = x_hat; tex_xbar_g = tex_xhat;
+        } else {
+            coll->all_gather_inplace(x_bar, xblock, stream);
+            if (compute_gap) coll->all_gather_inplace(x_tmp, xblock, stream);
+        }
     } else {
     if (iter == 0) { ResidualDualOp<false, true> o; fill_dual(o); launch_stream(AT, o, stream); }
     else if (compute_gap) { ResidualDualOp<true, false> o; fill_dual(o); launch_stream(AT, o, stream); }
@@ -1396,8 +1424,8 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(AT), 5, d_scal);
     }
     auto fill_primal = [&](auto &o) {
-        o.x_bar = x_bar; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
-        o.y_bar = y_bar; o.y_tmp = y_tmp; o.tex = tex_xbar; o.partials = d_partials;
+        o.x_bar = xbar_g; o.x_tmp = x_tmp; o.AL = AL; o.AU = AU; o.row_norm = row_norm; o.y_obj = y_obj;
+        o.y_bar = y_bar; o.y_tmp = y_tmp; o.tex = tex_xbar_g; o.partials = d_partials;
     };
     {
         ResidualPrimalOp<false> o; fill_primal(o); launch_stream(A, o, stream);
@@ -1408,7 +1436,8 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
         // restart gap terms <A dx, dy>, |dy|^2 (slots 7, 8) as a second single-product pass.  The two-product variant
         // (ResidualPrimalOp<true>) doubles the shared-memory staging; at 6 CTAs/SM that leaves ~28 KB of L1, i.e. hardly any
         // in-flight gather misses: measured 4.5 ms on C3 against 0.6 ms per single-product pass (same row sums bit for bit).
-        WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.tex = tex_xtmp; o.partials = d_partials;
+        if (push) { exchange_x(false, 3, x_tmp); xtmp_g = x_hat; tex_xtmp_g = tex_xhat; }   // all-gather of x_bar - x_hat (after the primal pass has read x_hat)
+        WeightedNormOp o; o.dx = xtmp_g; o.dy = y_tmp; o.tex = tex_xtmp_g; o.partials = d_partials;
         launch_stream(A, o, stream);
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal + 7);
         launches += 2;
@@ -1456,8 +1485,11 @@ void Engine::compute_residuals(int iter, bool compute_gap, Residuals *res, Resta
 
 // reference compute_weighted_norm, src/main_iterate.cu:486-515
 double Engine::weighted_norm_after_restart() {
-    if (dist()) coll->all_gather_inplace(x_tmp, xblock, stream);   // A dx needs every block of dx
-    WeightedNormOp o; o.dx = x_tmp; o.dy = y_tmp; o.tex = tex_xtmp; o.partials = d_partials;
+    const double *dxg = x_tmp;
+    cudaTextureObject_t dxt = tex_xtmp;
+    if (dist() && push_mode()) { exchange_x(false, 3, x_tmp); dxg = x_hat; dxt = tex_xhat; }   // A dx needs every block of dx
+    else if (dist()) coll->all_gather_inplace(x_tmp, xblock, stream);
+    WeightedNormOp o; o.dx = dxg; o.dy = y_tmp; o.tex = dxt; o.partials = d_partials;
     launch_stream(A, o, stream);
     final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
     sumsq_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(x_tmp + xb0, xb1 - xb0, d_partials);   // |dx|^2 over the owned block

@@ -152,7 +152,9 @@ class Engine {
     // coll == nullptr: single GPU.
     Collective *coll = nullptr;
     PeerExchange *px = nullptr;    // NVLink peer-memory exchange (collective.h); null: NCCL reduce-scatter + all-gather
-    void exchange_x(bool check, bool plain = false);   // reduce-scatter + x-update on the owned block + all-gather, by either transport
+    // reduce-scatter + x-update on the owned block + all-gather, by either transport (mode 0); modes 1-3: the other exchanges of the
+    // partitioned mode on the peer-memory transport (fused_exchange_x_kernel, engine.cu)
+    void exchange_x(bool check, int mode = 0, const double *src = nullptr);
     void partial_ATy_pass(const double *g = nullptr, cudaTextureObject_t tex = 0);   // w_p = A_p^T g_p (g = y by default) into wn, or (peer exchange) pushed into the owners' receive slots
     bool push_mode() const { return px != nullptr && AT.bands.empty(); }
     int nranks = 1, rank = 0, m_global = 0, row0 = 0;
