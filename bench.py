@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- HPR iterations/s of the B200-native engine on BASELINE.json's configs.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|small|c3band]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|small|c3band|c3block]
 
 One "step" = ITERS_PER_STEP (100) consecutive HPR iterations of the full driver (fused x/y phase kernels, the check
 iterations and residual passes the reference's schedule puts among them, restarts and sigma updates) on one synthetic
@@ -58,6 +58,9 @@ WORKLOADS = {
     # gathers coalesce into few sectors (shows what the kernels reach when the input has locality)
     "c3band": dict(kind="banded", m=2_000_000, n=5_000_000, nnz=100_000_000,
                    name="structured twin of configs[2]: banded LP m=2e6 n=5e6 nnz=1e8 (columns within a 4096-wide window)"),
+    # ... and on a BLOCK-structured one (dense 8x8 blocks): a warp's gathers coalesce into whole 64-byte segments in both passes
+    "c3block": dict(kind="blocked", m=2_000_000, n=5_000_000, nnz=100_000_000,
+                    name="block-structured twin of configs[2]: m=2e6 n=5e6 nnz=1e8, dense 8x8 blocks within a 4096-wide window"),
     "small": dict(kind="uniform", m=5_000, n=20_000, nnz=200_000, name="debug: uniform m=5e3 n=2e4 nnz=2e5"),
     # BASELINE.json configs[3]: solve_batched shared-A m=5e4 n=2e5 nnz=2e6, batch 256, batch-sharded over the GPUs
     "c4": dict(kind="uniform", m=50_000, n=200_000, nnz=2_000_000, batch=256, iters=300,
@@ -274,7 +277,7 @@ def run_engine_arm(args, pkg, spec, lp, local):
     # FMA on this launch shape (tools/gather_bench.cu, SPMV_TEX) = 262e9 nnz/s with the gathered vector resident in L2.
     port = None
     gc = ROOT / "profiles" / "r1_gather_ceiling.json"
-    if gc.exists() and spec["kind"] != "banded":
+    if gc.exists() and spec["kind"] not in ("banded", "blocked"):
         try:
             rows = [r for r in json.loads(gc.read_text())["results"] if r["mode"] == "SPMV_TEX"]
             vec = m if dom == "x" else n     # x-phase gathers y (m entries), y-phase gathers x_hat (n entries)

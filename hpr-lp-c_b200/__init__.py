@@ -507,7 +507,8 @@ SEED = 20251018
 
 def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
     """kind: 'uniform' | 'powerlaw' | 'banded' (uniform row lengths, columns of row i within a 4096-wide window around
-    i*n/m: the structured twin used to show the kernels on coalescing gathers). Returns the dict create_model() takes
+    i*n/m: gathers with cache locality) | 'blocked' (dense 8x8 blocks inside that window: gathers that coalesce into whole
+    64-byte segments in both passes). Returns the dict create_model() takes
     (+ x*,y*,z*,obj*)."""
     if not SYNTH_LIB_PATH.exists():
         raise FileNotFoundError(f"{SYNTH_LIB_PATH} not built")
@@ -518,7 +519,7 @@ def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
     L.synth_lp_matrix_rows.argtypes = [C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
     L.synth_lp_vectors.restype = C.c_double
     L.synth_lp_vectors.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, C.c_uint64, C.c_uint64] + [c_double_p] * 8
-    k = {"uniform": 0, "powerlaw": 1, "banded": 0}[kind]
+    k = {"uniform": 0, "powerlaw": 1, "banded": 0, "blocked": 0}[kind]
     rp = np.zeros(m + 1, np.int32)
     tot = L.synth_lp_rowptr(k, m, n, int(nnz), seed, _ip(rp))
     col = np.zeros(tot, np.int32); val = np.zeros(tot)
@@ -526,6 +527,10 @@ def synth_lp(kind, m, n, nnz, seed=SEED, vec_seed=None, with_solution=False):
         L.synth_lp_matrix_rows_banded.restype = None
         L.synth_lp_matrix_rows_banded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
         L.synth_lp_matrix_rows_banded(m, n, 4096, seed, _ip(rp), 0, m, _ip(col), _dp(val))
+    elif kind == "blocked":
+        L.synth_lp_matrix_rows_blocked.restype = None
+        L.synth_lp_matrix_rows_blocked.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, c_int_p, C.c_int, C.c_int, c_int_p, c_double_p]
+        L.synth_lp_matrix_rows_blocked(m, n, 4096, int(os.environ.get("SYNTH_BLOCK_RUN", "8")), seed, _ip(rp), 0, m, _ip(col), _dp(val))
     else:
         L.synth_lp_matrix_rows(n, seed, _ip(rp), 0, m, _ip(col), _dp(val))
     lp = dict(m=m, n=n, rowPtr=rp, colIndex=col, values=val)

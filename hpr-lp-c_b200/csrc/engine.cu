@@ -593,17 +593,32 @@ static void free_matrix(DevCsr &M) {
     M = DevCsr();
 }
 
-static int pick_lanes(double mean_len, const char *env_name) {
+static int pick_lanes(double mean_len, double len_cv, const char *env_name) {
     if (const char *e = getenv(env_name)) {
         const int g = atoi(e);
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
     }
-    // Lanes per row from the measured mean row length of this matrix.  Every extra lane costs shuffle
+    // Lanes per row from the measured row-length statistics of this matrix.  Every extra lane costs shuffle
     // wavefronts on the L1 data stage (the binding unit), so few lanes win: B200 sweep on C2/C3
     // (gpurun_out_14/15): mean 10 and 20 -> 1 lane best; mean 50 and 100 -> 8 lanes best (4 and 16 within 3 %).
-    if (mean_len < 28.0) return 1;
+    // With one lane per row the batch of 32 rows takes as long as its longest row, so rows of uneven length want lanes
+    // even when they are short on average (profiles/r2_lanes_vs_structure.md: mean 20, std/mean 0.63 -> 4 lanes 19 % faster,
+    // 0.45 -> 7 %, 0.32 -> 3 %; Poisson lengths of a uniformly random matrix, 0.22 -> 1 lane 5 % faster).
+    if (mean_len < 8.0) return 1;
+    if (mean_len < 28.0) return len_cv >= 0.4 ? 4 : 1;
     if (mean_len < 40.0) return 4;
     return 8;
+}
+
+// sum over rows of len^2 (exact, integer): the spread of the row lengths decides the lanes per row (pick_lanes)
+__global__ void row_len_sq_kernel(const int *rowPtr, int rows, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const unsigned long long len = (unsigned long long)(rowPtr[r + 1] - rowPtr[r]);
+        acc += len * len;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 void Engine::finish_matrix(DevCsr &M) {
@@ -612,11 +627,22 @@ void Engine::finish_matrix(DevCsr &M) {
     build_item_rows_kernel<int><<<(entries + threads - 1) / threads, threads, 0, stream>>>(M.rowPtr, M.rows, M.nnz, entries, M.item_row);
     launches++;
     const size_t part_bytes = sizeof(PartSlot) * (size_t)M.n_items * kWarps * 2;
+    M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
+    M.len_cv = 0.0;
+    if (M.rows > 0 && M.nnz > 0) {   // std/mean of the row lengths; the first packet slot is free scratch until it is armed below
+        unsigned long long sq = 0;
+        HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0, sizeof(PartSlot), stream));
+        row_len_sq_kernel<<<std::min((M.rows + threads - 1) / threads, 1184), threads, 0, stream>>>(M.rowPtr, M.rows, M.head_part);
+        launches++;
+        HPR_CUDA_CHECK(cudaMemcpyAsync(&sq, M.head_part, sizeof(sq), cudaMemcpyDeviceToHost, stream));
+        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const double var = (double)sq / (double)M.rows - M.mean_len * M.mean_len;
+        M.len_cv = var > 0.0 ? std::sqrt(var) / M.mean_len : 0.0;
+    }
     HPR_CUDA_CHECK(cudaMemsetAsync(M.head_part, 0xFF, part_bytes, stream));   // every packet "not published"
     HPR_CUDA_CHECK(cudaMemsetAsync(M.tail_part, 0xFF, part_bytes, stream));
     HPR_CUDA_CHECK(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned), stream));
     M.tickets_issued = 0;
-    M.mean_len = M.rows > 0 ? (double)M.nnz / (double)M.rows : 0.0;
 }
 
 // Column bands of M for passes whose gathered vector (M.cols doubles) does not fit the L2: 8-byte gathers from DRAM run at
@@ -674,7 +700,7 @@ void Engine::build_bands(DevCsr &M) {
     HPR_CUDA_CHECK(cudaStreamSynchronize(stream));   // ptrs (host vector) must outlive the copy
     for (int b = 0; b < nb; ++b) {
         finish_matrix(M.bands[b]);
-        M.bands[b].G = pick_lanes(M.bands[b].mean_len, "HPRLP_LANES_BAND");
+        M.bands[b].G = pick_lanes(M.bands[b].mean_len, M.bands[b].len_cv, "HPRLP_LANES_BAND");
     }
     M.carry = reinterpret_cast<double *>(store + o_carry);
     M.band_store = store;
@@ -722,8 +748,8 @@ void Engine::alloc_common() {
     tex_y = make_tex(y, m); tex_xhat = make_tex(x_hat, n);
     tex_q = make_tex(wm2, m); tex_atq = make_tex(wn, n);   // power iteration: q and A^T q
     tex_ybar = make_tex(y_bar, m); tex_xbar = make_tex(x_bar, n); tex_xtmp = make_tex(x_tmp, n);   // check passes
-    A.G = pick_lanes(A.mean_len, "HPRLP_LANES_A");
-    AT.G = pick_lanes(AT.mean_len, "HPRLP_LANES_AT");
+    A.G = pick_lanes(A.mean_len, A.len_cv, "HPRLP_LANES_A");
+    AT.G = pick_lanes(AT.mean_len, AT.len_cv, "HPRLP_LANES_AT");
 }
 
 // Host -> device copy of a large PAGEABLE array.  cudaMemcpyAsync from pageable memory is staged by the driver through one

@@ -46,8 +46,9 @@ struct DevCsr {
     unsigned *ticket = nullptr;             // chunk tickets handed out by csr_stream_kernel since the last zeroing (kernels.cuh)
     unsigned long long tickets_issued = 0;  // host count of the same: the counter is re-zeroed between launches before it can wrap
     int push_chunk0 = 0;    // first chunk of the row-partitioned push pass of this rank (kernels.cuh, CsrView::chunk_offset)
-    int G = 1;              // lanes per row in phase 2, from the mean row length
+    int G = 1;              // lanes per row in phase 2, from the row-length statistics (pick_lanes)
     double mean_len = 0.0;
+    double len_cv = 0.0;    // std/mean of the row lengths
     int max_len = 0;
     // Column bands (Engine::build_bands): when the gathered vector is larger than the L2 can hold, the passes over this
     // matrix run band by band over column slices that do fit, carrying the row sums in `carry` (rows doubles).

@@ -59,6 +59,7 @@ def lp_cases(pkg):
         "powerlaw": pkg.synth_lp("powerlaw", 4000, 9000, 120000),
         "edge": make_edge_lp(pkg),
         "toy": pkg.TOY_LP,
+        "blocked": pkg.synth_lp("blocked", 2400, 6000, 2400 * 50),   # dense 8x8 blocks: column counts are multiples of 8
     }
 
 
@@ -93,7 +94,7 @@ def test_scaling_matches_oracle(pkg, engine, oracle, name, flags):
     assert (ATs != As.T.tocsr()).nnz == 0
 
 
-@pytest.mark.parametrize("name", ["uniform", "powerlaw", "edge", "toy"])
+@pytest.mark.parametrize("name", ["uniform", "powerlaw", "edge", "toy", "blocked"])
 def test_first_1000_iterates_match_oracle(pkg, engine, oracle, name):
     lp = lp_cases(pkg)[name]
     trace = [10, 50, 150, 160, 300, 500, 1000]
@@ -104,6 +105,10 @@ def test_first_1000_iterates_match_oracle(pkg, engine, oracle, name):
     engine.free_model(model)
     want = oracle.solve(lp, p, power_z0=z0, trace_iters=trace)
     assert got["status"] == want["status"] == "ITER_LIMIT" and got["iter"] == 1000
+    if name == "blocked":     # short rows of uneven length (std/mean 0.6) take 4 lanes per row, even ones (uniform) 1
+        assert (got["info"]["lanes_A"], got["info"]["lanes_AT"]) == (8, 4)
+    if name == "uniform":
+        assert got["info"]["lanes_AT"] == 1
     assert abs(got["info"]["lambda_max"] - want["info"]["lambda_max"]) <= 1e-11 * want["info"]["lambda_max"]
     assert got["info"]["power_iters"] == want["info"]["power_iters"]
     assert got["info"]["restarts"] == want["info"]["restarts"]

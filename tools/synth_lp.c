@@ -22,6 +22,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -130,6 +131,44 @@ void synth_lp_matrix_rows_banded(int m, int n, int window, uint64_t seed, const 
                 if (c[k] == c[k - 1]) { c[k - 1] = (int)(lo + (long long)(rng(seed, 2 + 4 * (uint64_t)i, ctr++) % (uint64_t)w)); dup = 1; }
             if (!dup) break;
         }
+        uint64_t vctr = 0;
+        for (int k = 0; k < len; ++k) {
+            double v;
+            do { v = 2.0 * u01(rng(seed, 3 + 4 * (uint64_t)i, vctr++)) - 1.0; } while (fabs(v) < 1e-3);
+            val[p0 + k] = v;
+        }
+    }
+}
+
+/* "blocked" twin: dense run x run blocks.  The `run` rows of a row group share their columns, which come as runs of
+ * `run` consecutive columns (aligned to `run`) drawn from a `window`-wide slice around the group's diagonal position, so a
+ * warp's gathers coalesce into whole 64-byte segments in the pass over A and in the pass over the transpose. */
+void synth_lp_matrix_rows_blocked(int m, int n, int window, int run, uint64_t seed, const int *rowPtr, int r0, int r1, int *col, double *val) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = r0; i < r1; ++i) {
+        const int p0 = rowPtr[i], len = rowPtr[i + 1] - rowPtr[i];
+        int *c = col + p0;
+        const int g = i / run;
+        const int nb = (len + run - 1) / run;
+        int w = window < nb * run ? nb * run : window;
+        if (w > n) w = n;
+        long long lo = (long long)g * run * n / m - w / 2;
+        if (lo < 0) lo = 0;
+        if (lo + w > n) lo = n - w;
+        lo = lo / run * run;
+        const int wb = w / run;               /* block columns in the window */
+        int blk[64];
+        if (nb > 64 || nb > wb) { fprintf(stderr, "synth_lp blocked: row too long\n"); abort(); }
+        uint64_t ctr = 0;
+        for (int k = 0; k < nb; ++k) blk[k] = (int)(rng(seed, 2 + 4 * (uint64_t)g, ctr++) % (uint64_t)wb);
+        for (;;) {
+            qsort(blk, (size_t)nb, sizeof(int), cmp_int);
+            int dup = 0;
+            for (int k = 1; k < nb; ++k)
+                if (blk[k] == blk[k - 1]) { blk[k - 1] = (int)(rng(seed, 2 + 4 * (uint64_t)g, ctr++) % (uint64_t)wb); dup = 1; }
+            if (!dup) break;
+        }
+        for (int k = 0; k < len; ++k) c[k] = (int)(lo + (long long)blk[k / run] * run + k % run);
         uint64_t vctr = 0;
         for (int k = 0; k < len; ++k) {
             double v;
