@@ -520,12 +520,13 @@ void pinned_block_release(double *p) {
 
 // The engines' private stream-ordered pool, one per device, created on first use.
 namespace {
+constexpr int kMaxDevices = 64;
 std::mutex g_pool_mu;
-cudaMemPool_t g_pools[64] = {};
+cudaMemPool_t g_pools[kMaxDevices] = {};
 }
 static cudaMemPool_t engine_pool(int device) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (device < 0 || device >= 64) throw std::runtime_error("device number out of range");
+    if (device < 0 || device >= kMaxDevices) throw std::runtime_error("device number out of range");
     if (!g_pools[device]) {
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
@@ -539,7 +540,48 @@ static cudaMemPool_t engine_pool(int device) {
     }
     return g_pools[device];
 }
+// One cuRAND generator per device, kept across solves: creating and destroying one costs a device allocation, a free (a
+// device-wide synchronisation) and 1-250 ms of wall time per solve on the B200 boxes (HPRLP_TIMING, "power start vector").
+// Re-seeding and rewinding it reproduces the sequence of a fresh generator.
+struct CachedGenerator {
+    std::mutex mu;
+    curandGenerator_t gen = nullptr;
+};
+static CachedGenerator g_gens[kMaxDevices];
+
+// N(0,1) doubles of a fresh XORWOW generator with seed 1 (reference src/preprocess.cu:153-156), count even
+static void draw_power_start(int device, double *out, size_t count, cudaStream_t stream) {
+    if (device < 0 || device >= kMaxDevices) throw std::runtime_error("device number out of range");
+    CachedGenerator &c = g_gens[device];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.gen && curandCreateGenerator(&c.gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS) {
+        c.gen = nullptr;
+        throw std::runtime_error("curandCreateGenerator failed");
+    }
+    bool ok = curandSetStream(c.gen, stream) == CURAND_STATUS_SUCCESS;
+    ok = ok && curandSetPseudoRandomGeneratorSeed(c.gen, 1ULL) == CURAND_STATUS_SUCCESS;
+    ok = ok && curandSetGeneratorOffset(c.gen, 0ULL) == CURAND_STATUS_SUCCESS;
+    ok = ok && curandGenerateNormalDouble(c.gen, out, count, 0.0, 1.0) == CURAND_STATUS_SUCCESS;
+    const cudaError_t e = cudaStreamSynchronize(stream);   // the generator must not be re-seeded under a running draw
+    if (!ok || e != cudaSuccess) {
+        curandDestroyGenerator(c.gen);
+        c.gen = nullptr;
+        throw std::runtime_error("cuRAND draw of the power-iteration start vector failed");
+    }
+}
+
 void release_cached_device_memory() {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        std::lock_guard<std::mutex> lk(g_gens[d].mu);
+        if (g_gens[d].gen) {
+            cudaSetDevice(d);
+            curandDestroyGenerator(g_gens[d].gen);
+            g_gens[d].gen = nullptr;
+        }
+    }
+    cudaSetDevice(prev);
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (cudaMemPool_t p : g_pools)
         if (p) HPR_CUDA_CHECK(cudaMemPoolTrimTo(p, 0));
@@ -1145,13 +1187,7 @@ void warm_device(int device) {
     cudaFree(nullptr);   // context + module load
     double *buf = nullptr;
     if (cudaMalloc(&buf, 2 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
-    curandGenerator_t gen = nullptr;
-    if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) == CURAND_STATUS_SUCCESS) {
-        curandSetPseudoRandomGeneratorSeed(gen, 1ULL);
-        curandGenerateNormalDouble(gen, buf, 2, 0.0, 1.0);
-        cudaDeviceSynchronize();
-        curandDestroyGenerator(gen);
-    }
+    try { draw_power_start(device, buf, 2, nullptr); } catch (...) {}
     cudaFree(buf);
     try { engine_pool(device); } catch (...) {}
     cudaGetLastError();
@@ -1167,16 +1203,7 @@ void Engine::power_start_vector(double *d_z) {
         HPR_CUDA_CHECK(cudaMalloc(&gen_buf, sizeof(double) * (size_t)mg));
     }
     HPR_CUDA_CHECK(cudaMemsetAsync(gen_buf, 0, sizeof(double) * mg, stream));
-    if ((mg % 2) == 0) {
-        curandGenerator_t gen = nullptr;
-        if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
-            throw std::runtime_error("curandCreateGenerator failed");
-        curandSetStream(gen, stream);
-        curandSetPseudoRandomGeneratorSeed(gen, 1ULL);
-        curandGenerateNormalDouble(gen, gen_buf, (size_t)mg, 0.0, 1.0);
-        HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
-        curandDestroyGenerator(gen);
-    }
+    if ((mg % 2) == 0) draw_power_start(device, gen_buf, (size_t)mg, stream);
     if (dist()) {
         HPR_CUDA_CHECK(cudaMemcpyAsync(d_z, gen_buf + row0, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
         HPR_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1211,8 +1238,7 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
     launches += 2;
     allreduce(d_scal, 1);
     double lambda = 1.0;
-    int it;
-    for (it = 1; it <= max_iter; ++it) {
+    auto one_iteration = [&]() {
         power_normalize_kernel<<<vec_grid(m), kVecThreads, 0, stream>>>(z, q, d_scal, m);
         if (dist() && push_mode()) {   // A^T q = sum over row blocks: rows pushed to their owners, summed there, sent to everyone's x_hat
             partial_ATy_pass(q, tex_q);
@@ -1227,20 +1253,61 @@ double Engine::power_iteration(int max_iter, double tol, const double *host_z0, 
         final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, part_blocks(A), 2, d_scal);
         allreduce(d_scal, 2);
         launches += 4;
-        if (it % 10 == 0) {
-            power_error_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, q, d_scal + 1, m, d_partials);
-            final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
-            launches += 2;
-            allreduce(d_scal + 2, 1);
+    };
+    auto error_estimate = [&]() {   // every 10th iteration, like the reference
+        power_error_kernel<<<kVecBlocks, kVecThreads, 0, stream>>>(z, q, d_scal + 1, m, d_partials);
+        final_reduce_kernel<<<1, 1024, 0, stream>>>(d_partials, kVecBlocks, 1, d_scal + 2);
+        launches += 2;
+        allreduce(d_scal + 2, 1);
+    };
+    // Small matrices are launch-bound here (configs[3]: 1640 iterations of four 5-10 us kernels): ten iterations and their
+    // error estimate replay as one graph once the first 30 have run directly (an LP that converges at once never pays the
+    // instantiation).  Same kernels, same arguments, same order: the result does not depend on the path.
+    static const bool no_graph = getenv("HPRLP_NO_GRAPH") != nullptr;
+    const bool graph_ok = !no_graph && !dist() && nnz <= 4000000 && A.bands.empty() && AT.bands.empty();
+    constexpr int kPowerGraphKey = -10;   // graphs_ keys > 0 are loop graphs (run_normal)
+    int it = 0;
+    bool converged = false;
+    while (it < max_iter) {
+        const int blk = std::min(10, max_iter - it);
+        if (blk == 10 && graph_ok && it >= 30) {
+            auto g = graphs_.find(kPowerGraphKey);
+            if (g == graphs_.end()) {
+                cudaGraph_t gr = nullptr;
+                cudaGraphExec_t ge = nullptr;
+                HPR_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                const long long before = launches;
+                for (int i = 0; i < 10; ++i) one_iteration();
+                error_estimate();
+                launches = before;
+                HPR_CUDA_CHECK(cudaStreamEndCapture(stream, &gr));
+                HPR_CUDA_CHECK(cudaGraphInstantiate(&ge, gr, nullptr, nullptr, 0));
+                cudaGraphDestroy(gr);
+                g = graphs_.emplace(kPowerGraphKey, ge).first;
+            }
+            for (DevCsr *M : {&A, &AT}) {   // ten launches per matrix inside the graph: keep the ticket bookkeeping exact
+                if (M->tickets_issued + 10ull * M->n_items > ticket_wrap()) {
+                    HPR_CUDA_CHECK(cudaMemsetAsync(M->ticket, 0, sizeof(unsigned), stream));
+                    M->tickets_issued = 0;
+                }
+                M->tickets_issued += 10ull * M->n_items;
+            }
+            HPR_CUDA_CHECK(cudaGraphLaunch(g->second, stream));
+            launches += 42;
+        } else {
+            for (int i = 0; i < blk; ++i) one_iteration();
+            if (blk == 10) error_estimate();
+        }
+        it += blk;
+        if (blk == 10) {
             const double ts0 = timing ? now_seconds() : 0.0;
             fetch_scalars(3);
             if (timing) { const double d = now_seconds() - ts0; t_sync += d; t_sync_max = std::max(t_sync_max, d); }
             lambda = h_scal[1];
-            if (sqrt(h_scal[2]) < tol) break;
+            if (sqrt(h_scal[2]) < tol) { converged = true; break; }
         }
     }
-    if (it > max_iter) {
-        it = max_iter;
+    if (!converged) {
         printf("Power iteration did not converge within the specified tolerance.\nMax iter: %d, Error: %.2e\n", max_iter,
                sqrt(h_scal[2]));
     }
