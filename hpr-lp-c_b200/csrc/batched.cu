@@ -925,6 +925,39 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         S.d_dd = reinterpret_cast<DD *>(base + o_dd); S.d_norms = reinterpret_cast<double *>(base + o_norms);
         S.d_raw = reinterpret_cast<double *>(base + o_raw);
     }
+    S.h_scal_doubles = (size_t)kMaxSlots * S.Bpad;
+    S.h_scal = bpinned_acquire(S.h_scal_doubles);
+    stage_done("state allocation");
+
+    // The power iteration needs the shared, scaled matrix only (reference :994-1001 runs it after the instances are built):
+    // it runs on the engine's stream from a helper thread while this thread stages and scales the instances on a second
+    // stream.  On configs[3] both take 0.04-0.06 s and the iteration's small kernels leave the copy engines and most SMs idle.
+    struct UploadStream {
+        cudaStream_t s = nullptr;
+        cudaEvent_t ready = nullptr;
+        ~UploadStream() { if (ready) cudaEventDestroy(ready); if (s) cudaStreamDestroy(s); }
+    } upl;
+    HPR_CUDA_CHECK(cudaStreamCreateWithFlags(&upl.s, cudaStreamNonBlocking));
+    HPR_CUDA_CHECK(cudaEventCreateWithFlags(&upl.ready, cudaEventDisableTiming));
+    HPR_CUDA_CHECK(cudaEventRecord(upl.ready, st));          // matrix scaling and the arena's zero-fill are queued on st
+    HPR_CUDA_CHECK(cudaStreamWaitEvent(upl.s, upl.ready, 0));
+    double power_time = 0.0;
+    std::exception_ptr power_error;
+    std::thread power_thread([&]() {
+        try {
+            HPR_CUDA_CHECK(cudaSetDevice(actual.device_number));
+            const double t0 = now_s();
+            S.lambda_max = S.eng.power_iteration(5000, 1.0e-4, nullptr, nullptr) * 1.01;
+            power_time = now_s() - t0;
+        } catch (...) { power_error = std::current_exception(); }
+    });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } power_joiner{power_thread};
+    const cudaStream_t eng_st = st;
+    st = upl.s;   // the instance stage below runs on the upload stream
+
     // host array (rows x B values) -> column-major staging buffer on the device
     auto stage_in = [&](double *dst, const double *host, int rows) {
         const size_t bytes = sizeof(double) * (size_t)rows * B;
@@ -933,10 +966,6 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
         rowmajor_to_colmajor_kernel<<<dim3((rows + 31) / 32, (B + 31) / 32), 256, 0, st>>>(S.d_raw, dst, rows, B);
         S.launches++;
     };
-    S.h_scal_doubles = (size_t)kMaxSlots * S.Bpad;
-    S.h_scal = bpinned_acquire(S.h_scal_doubles);
-
-    stage_done("state allocation");
     // per-instance scaling on the device -- reference build_batched_lp_device :792-885.  Inputs are staged straight from
     // the caller's (pageable) arrays by several host threads; no host copies, no host loops over B x (n + m) entries.
     const dim3 norm_grid(kNormChunks, B);
@@ -975,11 +1004,9 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     S.obj_constants.assign(B, model->obj_constant);
     if (obj_constants) S.obj_constants.assign(obj_constants, obj_constants + B);
     stage_done("instance upload + scaling");
-
-    // power iteration on the shared, scaled matrix -- reference :994-1001
-    const double power_start = now_s();
-    S.lambda_max = S.eng.power_iteration(5000, 1.0e-4, nullptr, nullptr) * 1.01;
-    const double power_time = now_s() - power_start;
+    st = eng_st;
+    power_thread.join();
+    if (power_error) std::rethrow_exception(power_error);
 
     RestartHost R;
     R.restart_flag.assign(B, 0); R.first_restart.assign(B, 1); R.inner.assign(B, 0); R.times.assign(B, 0);
@@ -997,7 +1024,37 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     HPR_CUDA_CHECK(cudaMemcpy(S.d_scale_c, cs_pad.data(), sizeof(double) * S.Bpad, cudaMemcpyHostToDevice));
     HPR_CUDA_CHECK(cudaMemcpy(S.d_active, act_pad.data(), S.Bpad, cudaMemcpyHostToDevice));
     const double setup_time = now_s() - setup_start;
-    stage_done("power iteration + scalars");
+    stage_done("power iteration (rest) + scalars");
+
+    // Result arrays (reference collect_results :887-935 allocates them after the loop): allocated now and touched by helper
+    // threads while the GPU iterates, so the device-to-host copies at the end do not pay a page fault per 4 KB of fresh memory
+    // (0.92 GB of results on configs[3]).
+    struct OutArrays {
+        double *x = nullptr, *y = nullptr, *z = nullptr;
+        ~OutArrays() { std::free(x); std::free(y); std::free(z); }
+    } outs;
+    outs.x = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    outs.y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)m * B));
+    outs.z = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    if (!outs.x || !outs.y || !outs.z) throw std::bad_alloc();
+    std::vector<std::thread> prefault;
+    struct JoinAll {
+        std::vector<std::thread> &ts;
+        ~JoinAll() { for (auto &t : ts) if (t.joinable()) t.join(); }
+    } prefault_joiner{prefault};
+    if (sizeof(double) * ((size_t)2 * n + m) * B >= ((size_t)64 << 20)) {
+        auto touch = [](double *p, size_t bytes, int part, int parts) {
+            volatile char *c = reinterpret_cast<volatile char *>(p);
+            const size_t lo = (bytes / parts * part) & ~(size_t)4095, hi = part + 1 == parts ? bytes : ((bytes / parts * (part + 1)) & ~(size_t)4095);
+            for (size_t o = lo; o < hi; o += 4096) c[o] = 0;
+        };
+        for (int t = 0; t < 4; ++t)
+            prefault.emplace_back([&, t]() {
+                touch(outs.x, sizeof(double) * (size_t)n * B, t, 4);
+                touch(outs.z, sizeof(double) * (size_t)n * B, t, 4);
+                touch(outs.y, sizeof(double) * (size_t)m * B, t, 4);
+            });
+    }
 
     const double solve_start = now_s();
     ResidualHost res;
@@ -1104,9 +1161,8 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     // collect_results (reference :887-935): unscale on the device, one D2H per output array
     HPRLP_batched_results out;
     out.m = m; out.n = n; out.batch_size = B;
-    out.x = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
-    out.y = static_cast<double *>(std::malloc(sizeof(double) * (size_t)m * B));
-    out.z = static_cast<double *>(std::malloc(sizeof(double) * (size_t)n * B));
+    for (auto &t : prefault) t.join();
+    out.x = outs.x; out.y = outs.y; out.z = outs.z;   // still owned by `outs` until the copies below have succeeded
     out.primal_obj = static_cast<double *>(std::malloc(sizeof(double) * B));
     out.residuals = static_cast<double *>(std::malloc(sizeof(double) * B));
     out.gap = static_cast<double *>(std::malloc(sizeof(double) * B));
@@ -1132,6 +1188,7 @@ static HPRLP_batched_results solve_batched_on_device(const LP_info_cpu *model, i
     out.power_time = power_time;
     out.time = setup_time + solve_time;
     stage_done("collect results");
+    outs.x = outs.y = outs.z = nullptr;   // handed to the caller (free_batched_results)
     return out;
 }
 
