@@ -414,7 +414,17 @@ static void launch_one(const CsrView<int> &v, const Op &op, cudaStream_t st) {
         }
         *v.issued_host += (unsigned long long)v.n_items;
     }
-    csr_stream_kernel<Op, G, int><<<v.n_items, kThreads, bytes, st>>>(v, op);
+    // programmatic stream serialization: the grid may become resident while the previous kernel of the stream drains
+    // (kernels.cuh: its CTAs wait at griddepcontrol.wait before touching anything an earlier kernel wrote)
+    static const bool pdl = getenv("HPRLP_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)v.n_items); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl_in_graphs = getenv("HPRLP_NO_PDL_GRAPH") == nullptr;   // captured launches become programmatic edges
+    cfg.attrs = attr; cfg.numAttrs = (pdl && (cap == cudaStreamCaptureStatusNone || pdl_in_graphs)) ? 1 : 0;
+    HPR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, csr_stream_kernel<Op, G, int>, v, op));
 }
 
 template <class Op>

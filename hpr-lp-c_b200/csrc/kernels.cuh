@@ -227,8 +227,15 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     if (threadIdx.x == 0) chunk_s = (atomicAdd(M.ticket, 1u) % gridDim.x + (unsigned)M.chunk_offset) % gridDim.x;
 #endif
     if (threadIdx.x < kWarps * 4) cta_part[threadIdx.x] = kPartEmpty;
+    // Programmatic dependent launch (launch_one sets the attribute; without it both instructions do nothing): the next
+    // kernel of the stream may fill the SM slots this grid's last wave leaves free.  Its CTAs draw their tickets and stop at
+    // the wait until this grid has completed and its writes are visible; nothing above the wait depends on an earlier kernel.
+    // The trigger comes after the barrier, i.e. after this CTA's ticket has RETURNED: a dependent launch on the same matrix
+    // draws from the same counter, and a launch must own n_items consecutive tickets.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     op.init();         // its loads (sigma, Halpern counter) do not depend on the chunk: in flight under the ticket's round trip
     __syncthreads();   // the only CTA barrier: before any work, so no warp ever waits for a slower one
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int chunk = (int)chunk_s;
 
     auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
