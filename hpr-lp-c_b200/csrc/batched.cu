@@ -19,7 +19,6 @@
 // Host logic (per-instance scaling with long-double norms, +-inf -> +-1e100, restart rules, sigma
 // update, `<=` stopping test, shared lambda_max bumped by max) restates the reference line by line.
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -201,129 +200,6 @@ HPR_UNROLL_(HPR_B_UNROLL)
         for (int q = 0; q < NG; ++q) op.row(r, q, acc[q], pre[q]);
         r = rn; p0 = np0; p1 = np1; c = nc; v = nv;
     }
-    op.finish(red, warp, lane);
-}
-
-// ---------------------------------------------------------------------------------------------
-// the same pass with the gathers staged through shared memory by cp.async (r2, late)
-// ---------------------------------------------------------------------------------------------
-// ncu stall sampling of batched_rows_kernel: 83 % long_scoreboard -- the passes are latency-bound, and every load a warp
-// keeps in flight costs it a register pair, i.e. occupancy (profiles/r2_batched_group_sweep.md).  Here a gather is a
-// cp.async of the lane's 8 bytes into a per-warp ring in shared memory: loads in flight cost no registers, so a warp runs
-// kNBuf-1 chunks of kCh nonzeros (the next row(s) included) ahead of the chunk it is summing.  Lane t of a chunk also parks
-// the matrix value of nonzero t in the ring (read back as a broadcast), so the consumer needs no shuffles.  Epilogue
-// operands are requested one row ahead.  Same arithmetic in the same order as batched_rows_kernel: identical results.
-#ifndef HPR_B_CH
-#define HPR_B_CH 8
-#endif
-#ifndef HPR_B_NBUF
-#define HPR_B_NBUF 3
-#endif
-#ifndef HPR_B_AMINB
-#define HPR_B_AMINB 4
-#endif
-constexpr int kCh = HPR_B_CH, kNBuf = HPR_B_NBUF;
-static_assert(32 % kCh == 0 && kNBuf >= 2, "chunks must not straddle a 32-nonzero block");
-static_assert(kRowsPerCta <= 32 * kBWarps, "a warp's row extents live one per lane");
-constexpr size_t kAsyncSmem = (size_t)kBWarps * kNBuf * kCh * (kGS + 1) * sizeof(double) + (size_t)kBWarps * kNBuf * sizeof(int);
-
-__device__ __forceinline__ void cp_async8_keep(double *smem_dst, const double *src, unsigned long long pol) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <class Op>
-__global__ void __launch_bounds__(kBThreads, HPR_B_AMINB) batched_rows_async_kernel(BView M, Op op, int G) {
-    static_assert(Op::kNG == 1, "one instance group per pass");
-    extern __shared__ __align__(16) unsigned char async_smem[];
-    __shared__ double red[kBWarps][kMaxSlots][kGS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *ring = reinterpret_cast<double *>(async_smem) + (size_t)warp * kNBuf * kCh * kGS;             // [buf][t][lane]
-    double *vals = reinterpret_cast<double *>(async_smem) + (size_t)kBWarps * kNBuf * kCh * kGS + (size_t)warp * kNBuf * kCh;   // [buf][t]
-    int *meta = reinterpret_cast<int *>(reinterpret_cast<double *>(async_smem) + (size_t)kBWarps * kNBuf * kCh * (kGS + 1)) + warp * kNBuf;
-    op.init(blockIdx.y, lane, G);
-    const unsigned long long keep = make_keep_policy();
-    const double *gbase = op.gp[0];
-    const int row0 = blockIdx.x * kRowsPerCta;
-    const int row1 = min(M.rows, row0 + kRowsPerCta);
-    const int first = row0 + warp;
-    const int nrows = first < row1 ? (row1 - first + kBWarps - 1) / kBWarps : 0;   // rows of this warp: first, first+8, ...
-    int e0 = 0, e1 = 0;                                                             // lane j: extent of the warp's j-th row
-    if (lane < nrows) { e0 = M.rowPtr[first + lane * kBWarps]; e1 = M.rowPtr[first + lane * kBWarps + 1]; }
-
-    // ---- producer state: row ir of the warp, next nonzero ip of [ip0, ip1); (c, v) = nonzeros blk .. blk+31 of the matrix
-    int ir = 0, ip0 = 0, ip1 = 0, ip = 0, blk = 0, c = 0, nc = 0;
-    double v = 0.0, nv = 0.0;
-    auto load_block = [&](int at, int end, int &cc, double &vv) {
-        cc = 0; vv = 0.0;
-        if (at + lane < end) { cc = __ldg(M.col + at + lane); vv = __ldg(M.val + at + lane); }
-    };
-    if (nrows > 0) {
-        ip0 = __shfl_sync(0xffffffffu, e0, 0); ip1 = __shfl_sync(0xffffffffu, e1, 0);
-        ip = blk = ip0;
-        load_block(ip0, ip1, c, v);
-        if (nrows > 1) load_block(__shfl_sync(0xffffffffu, e0, 1), __shfl_sync(0xffffffffu, e1, 1), nc, nv);
-    }
-    auto produce = [&](int b) {   // stage the next chunk into ring slot b (or an empty group when the rows are used up)
-        if (ir >= nrows) {
-            if (lane == 0) meta[b] = -1;
-            cp_async_commit();
-            return;
-        }
-        if (ip - blk == 32) { blk = ip; load_block(blk, ip1, c, v); }   // rows longer than 32 nonzeros: next block
-        const int off = ip - blk;
-        const int cnt = min(kCh, ip1 - ip);
-#pragma unroll
-        for (int t = 0; t < kCh; ++t) {
-            const int cc = __shfl_sync(0xffffffffu, c, (off + t) & 31);
-            if (t < cnt) cp_async8_keep(ring + ((size_t)b * kCh + t) * kGS + lane, gbase + (size_t)cc * kGS, keep);
-        }
-        if (lane >= off && lane < off + cnt) vals[b * kCh + lane - off] = v;
-        cp_async_commit();
-        ip += cnt;
-        const bool last = ip >= ip1;
-        if (lane == 0) meta[b] = cnt | (last ? 0x100 : 0);
-        if (last) {   // next row: its first block was requested when this row started
-            ++ir;
-            if (ir < nrows) {
-                ip0 = __shfl_sync(0xffffffffu, e0, ir); ip1 = __shfl_sync(0xffffffffu, e1, ir);
-                ip = blk = ip0; c = nc; v = nv;
-                if (ir + 1 < nrows) load_block(__shfl_sync(0xffffffffu, e0, ir + 1), __shfl_sync(0xffffffffu, e1, ir + 1), nc, nv);
-            }
-        }
-    };
-
-    // ---- consumer
-#pragma unroll
-    for (int b = 0; b < kNBuf - 1; ++b) produce(b);
-    int cr = first;                                   // row being summed
-    typename Op::Pre pre{};
-    if (nrows > 0) pre = op.pre(cr, 0);
-    double acc = 0.0;
-    for (int i = 0;; ++i) {
-        const int b = i % kNBuf;
-        produce((i + kNBuf - 1) % kNBuf);
-        cp_async_wait<kNBuf - 1>();                   // chunk i has landed
-        __syncwarp();
-        const int mt = meta[b];
-        if (mt < 0) break;
-        const int cnt = mt & 0xff;
-#pragma unroll
-        for (int t = 0; t < kCh; ++t)
-            if (t < cnt) acc = fma(vals[b * kCh + t], ring[((size_t)b * kCh + t) * kGS + lane], acc);
-        if (mt & 0x100) {
-            const int rn = cr + kBWarps;
-            typename Op::Pre pn{};
-            if (rn < row1) pn = op.pre(rn, 0);        // next row's epilogue operands: in flight under its chunks
-            op.row(cr, 0, acc, pre);
-            pre = pn; cr = rn; acc = 0.0;
-        }
-        __syncwarp();                                 // slot b is refilled by the produce() of the next-but-(kNBuf-2) round
-    }
-    cp_async_wait<0>();
     op.finish(red, warp, lane);
 }
 
@@ -865,32 +741,13 @@ class BatchedSolver {
     }
     double hs(int slot, int k) const { return h_scal[(size_t)slot * Bpad + k]; }
 
-    // every pass goes through here: cp.async-staged gathers (default) or the register-gather kernel
-    template <class Op>
-    void launch_rows(dim3 grid, const BView &view, const Op &op) {
-        static const bool staged = getenv("HPRLP_BATCH_REG_GATHER") == nullptr;
-        if constexpr (Op::kNG == 1) {
-            if (staged) {
-                static std::atomic<unsigned> configured{0};   // per instantiation, one bit per device
-                int dev = 0;
-                cudaGetDevice(&dev);
-                if (!(configured.load() & (1u << dev))) {
-                    HPR_CUDA_CHECK(cudaFuncSetAttribute(batched_rows_async_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsyncSmem));
-                    configured.fetch_or(1u << dev);
-                }
-                batched_rows_async_kernel<<<grid, kBThreads, kAsyncSmem, stream>>>(view, op, G);
-                return;
-            }
-        }
-        batched_rows_kernel<<<grid, kBThreads, 0, stream>>>(view, op, G);
-    }
     template <bool CHECK, int NG>
     void launch_x() {
         BXOp<CHECK, NG> ox{};
         ox.gcols = m; ox.orows = n;
         ox.Y = Y; ox.X = X; ox.X_hat = X_hat; ox.L = L; ox.U = U; ox.C = C; ox.lastX = lastX;
         ox.DX = DX; ox.Z_bar = Z_bar; ox.X_bar = X_bar; ox.sigma = d_sigma; ox.kx = d_k; ox.ky = d_k + Bpad; ox.active = d_active;
-        launch_rows(gridAT(NG), viewAT(), ox);
+        batched_rows_kernel<<<gridAT(NG), kBThreads, 0, stream>>>(viewAT(), ox, G);
     }
     template <bool CHECK, int NG>
     void launch_y() {
@@ -898,7 +755,7 @@ class BatchedSolver {
         oy.gcols = n; oy.orows = m;
         oy.X_hat = X_hat; oy.Y = Y; oy.AL = AL; oy.AU = AU; oy.lastY = lastY; oy.DY = DY; oy.Y_bar = Y_bar; oy.Y_obj = Y_obj;
         oy.sigma = d_sigma; oy.ky = d_k + Bpad; oy.kx = d_k; oy.active = d_active; oy.lambda_max = lambda_max;
-        launch_rows(gridA(NG), viewA(), oy);
+        batched_rows_kernel<<<gridA(NG), kBThreads, 0, stream>>>(viewA(), oy, G);
     }
     void iteration(bool check) {
         if (check) { launch_x<true, 1>(); launch_y<true, 1>(); }   // 1 in 10 iterations at most: one instantiation each
@@ -912,7 +769,7 @@ class BatchedSolver {
     // reference compute_weighted_norm :625-650 (lambda_max shared by the batch, only ever increased)
     std::vector<double> weighted_norm(const std::vector<double> &sigma) {
         BWeightedOp o{}; o.gcols = n; o.orows = m; o.DX = DX; o.DY = DY; o.partials = d_partials;
-        launch_rows(gridA(), viewA(), o);
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), o, G);
         batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal);
         batched_sumsq_kernel<<<dim3(nbx_vec, G), kBThreads, 0, stream>>>(DX, n, d_partials);
         batched_final_reduce_kernel<<<G, 32, 0, stream>>>(d_partials, nbx_vec, 1, Bpad, d_scal + 2 * (size_t)Bpad);
@@ -937,16 +794,16 @@ class BatchedSolver {
         if (iter == 0) {
             BResDualOp<true> o{}; o.gcols = m; o.orows = n; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
             o.col_norm = eng.col_norm; o.partials = d_partials;
-            launch_rows(gridAT(), viewAT(), o);
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o, G);
         } else {
             BResDualOp<false> o{}; o.gcols = m; o.orows = n; o.Y_bar = Y_bar; o.C = C; o.Z_bar = Z_bar; o.X_bar = X_bar; o.L = L; o.U = U;
             o.col_norm = eng.col_norm; o.partials = d_partials;
-            launch_rows(gridAT(), viewAT(), o);
+            batched_rows_kernel<<<gridAT(), kBThreads, 0, stream>>>(viewAT(), o, G);
         }
         batched_final_reduce_kernel<<<G, 32 * 4, 0, stream>>>(d_partials, nbx_AT, 4, Bpad, d_scal);
         BResPrimalOp p{}; p.gcols = n; p.orows = m; p.X_bar = X_bar; p.AL = AL; p.AU = AU; p.row_norm = eng.row_norm; p.Y_obj = Y_obj; p.Y_bar = Y_bar;
         p.partials = d_partials;
-        launch_rows(gridA(), viewA(), p);
+        batched_rows_kernel<<<gridA(), kBThreads, 0, stream>>>(viewA(), p, G);
         batched_final_reduce_kernel<<<G, 32 * 2, 0, stream>>>(d_partials, nbx_A, 2, Bpad, d_scal + 4 * (size_t)Bpad);
         launches += 4;
         fetch(6);
