@@ -62,6 +62,11 @@ constexpr int kBWarps = kBThreads / 32;
 constexpr int kRowsPerCta = HPR_B_ROWS;    // rows per CTA (8 warps): the software pipeline of the row loop needs a few rows per warp to fill
 constexpr double kInfReplacement = 1.0e100;   // reference src/batched_solver.cu:17
 
+#ifndef HPR_B_SMEM_BCAST
+#define HPR_B_SMEM_BCAST 1
+#endif
+struct alignas(16) BPair { double v; int c; int pad; };
+
 struct BView {
     int rows;          // rows of this matrix
     int gcols;         // rows of the gathered dense operand (= columns of this matrix)
@@ -105,6 +110,9 @@ template <class Op>
 __global__ void __launch_bounds__(kBThreads, Op::kNG >= 4 ? 3 : (Op::kNG == 2 ? 4 : HPR_B_MINB)) batched_rows_kernel(BView M, Op op, int G) {
     constexpr int NG = Op::kNG;
     __shared__ double red[kBWarps][kMaxSlots][kGS];
+#if HPR_B_SMEM_BCAST
+    __shared__ BPair pairs[kBWarps][32];
+#endif
     const int g0 = blockIdx.y * NG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     op.init(g0, lane, G);
@@ -173,6 +181,19 @@ HPR_UNROLL_(HPR_B_UNROLL)
                 v = (kk < p1) ? __ldg(M.val + kk) : 0.0;
             }
             const int cnt = min(32, p1 - k0);
+#if HPR_B_SMEM_BCAST
+            // the 32 (col, val) pairs of the block go through shared memory: one 16-byte broadcast read per nonzero instead
+            // of three shuffles (a 64-bit value is two) on the L1 data stage
+            __syncwarp();
+            pairs[warp][lane] = BPair{v, c, 0};
+            __syncwarp();
+HPR_UNROLL_(HPR_B_UNROLL)
+            for (int t = 0; t < cnt; ++t) {
+                const BPair pr = pairs[warp][t];
+#pragma unroll
+                for (int q = 0; q < NG; ++q) op.accum(pr.v, pr.c, q, acc[q], keep);
+            }
+#else
 HPR_UNROLL_(HPR_B_UNROLL)
             for (int t = 0; t < cnt; ++t) {
                 const int cc = __shfl_sync(0xffffffffu, c, t);
@@ -180,6 +201,7 @@ HPR_UNROLL_(HPR_B_UNROLL)
 #pragma unroll
                 for (int q = 0; q < NG; ++q) op.accum(vv, cc, q, acc[q], keep);
             }
+#endif
 #if HPR_B_PIPE == 1
             if (k0 == p0 && np0 + lane < np1) { nc = __ldg(M.col + np0 + lane); nv = __ldg(M.val + np0 + lane); }
 #endif
