@@ -49,9 +49,6 @@ constexpr int kWarps = kThreads / 32;
 #ifndef HPR_MIN_BLOCKS
 #define HPR_MIN_BLOCKS 6
 #endif
-#ifndef HPR_STAGE_OPERANDS
-#define HPR_STAGE_OPERANDS 1   // x-/y-phase: epilogue operands prefetched into shared memory by cp.async (0: loaded after the row sums)
-#endif
 #ifndef HPR_TEX_GATHER
 #define HPR_TEX_GATHER 1
 #endif
@@ -204,10 +201,9 @@ __device__ __forceinline__ double combine(double a, double b) { return MAX ? fma
 // Dynamic shared memory: kWarps * NV * kWarpChunk doubles (product slices) + reduction scratch.
 // ------------------------------------------------------------------------------------------------
 template <class Op>
-__host__ __device__ constexpr size_t stream_smem_bytes() {
+constexpr size_t stream_smem_bytes() {
     return sizeof(double) * ((size_t)kWarps * Op::NV * kWarpChunk + (size_t)kMaxSlots * kWarps) +
-           (HPR_BULK_STREAM ? (size_t)kWarps * (sizeof(int) * kWarpChunk + 16) : 0) +   // + column-index stage and one mbarrier per warp
-           sizeof(double) * (size_t)kWarps * Op::kStage * 32;                            // + staged epilogue operands (last)
+           (HPR_BULK_STREAM ? (size_t)kWarps * (sizeof(int) * kWarpChunk + 16) : 0);   // + column-index stage and one mbarrier per warp
 }
 
 template <class Op, int G, typename RP>
@@ -242,14 +238,9 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int chunk = (int)chunk_s;
 
-    constexpr int KS = Op::kStage;
-    // staged epilogue operands of the first 32 rows of this item: [warp][operand][lane], lane L <-> row rA + L
-    double *stage = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(smem) + stream_smem_bytes<Op>()) - (size_t)kWarps * KS * 32 +
-                    (size_t)warp * KS * 32 + lane;
-    auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1, bool staged) {
+    auto complete_row = [&](int r, double (&t)[NV], long long q0, long long q1) {
         if (M.carry_in) t[0] += M.carry_in[r];
         if (M.carry_out) M.carry_out[r] = t[0];
-        else if constexpr (KS > 0) { if (staged) op.row_staged(r, t, stage); else op.row(r, t, q0, q1); }
         else op.row(r, t, q0, q1);
     };
     const int item = chunk * kWarps + warp;
@@ -266,10 +257,6 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     if (rA + lane <= r_last) {
         p0 = (long long)M.rowPtr[rA + lane];
         p1 = (long long)M.rowPtr[rA + lane + 1];
-    }
-    if constexpr (KS > 0) {   // epilogue operands of those rows: in flight under phase 1, landing in shared memory
-        if (!M.carry_out && rA + lane <= r_last) op.stage(rA + lane, stage);
-        asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     // ---- phase 1: stream nonzeros, gather, multiply (kRoundNnz loads in flight per lane) -----------
@@ -377,16 +364,13 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
             }
         }
 
-        if constexpr (KS > 0) {
-            if (base == rA) asm volatile("cp.async.wait_group 0;" ::: "memory");   // each lane reads back what it copied itself
-        }
         // lane-parallel epilogue.  A row cut by an item boundary is finished by the item that holds its end (below);
         // the other items it spans only publish their partial sums.
         if (valid) {
             const bool head = (r == rA) && (p0 < s);   // row entered this item from the left (lane 0, first batch)
             const bool cont = (p1 > e);                // row continues to the right
             if (!head && !cont) {
-                complete_row(r, tot, p0, p1, base == rA);
+                complete_row(r, tot, p0, p1);
             } else if (head && !cont) {                // finished below; park this item's share (no live registers)
 #pragma unroll
                 for (int q = 0; q < NV; ++q) own_part[warp * 2 + q] = tot[q];
@@ -443,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
                 for (int q = 0; q < NV; ++q) sum[q] = combine<MX>(sum[q], __shfl_xor_sync(0xffffffffu, sum[q], off));
             }
         }
-        if (lane == 0) complete_row(rA, sum, P0, P1, true);
+        if (lane == 0) complete_row(rA, sum, P0, P1);
     }
     if (!M.carry_out) op.finish(red_scratch, chunk);   // (warp-uniform: kernel argument); partials indexed by chunk: deterministic
 }
@@ -482,17 +466,9 @@ __device__ __forceinline__ double gather_tex_or_ldg(cudaTextureObject_t tex, con
 struct OpBase {
     static constexpr int NV = 1;
     static constexpr bool kMax = false;
-    static constexpr int kStage = 0;   // epilogue operands per row that the kernel stages in shared memory ahead of phase 1
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ void finish(double *, int) {}
-    __device__ __forceinline__ void stage(int, double *) const {}
 };
-
-// one 8-byte asynchronous copy global -> shared (no register, no scoreboard entry while it is in flight)
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-}
 
 // x-phase (reference fused_update_x_z_rows_*_kernel, HPR_cuda_kernels.cu:297-361; check variant
 // update_zx_check_kernel :203-226):  w = (A^T y)_j ; zt = x + sigma (w - c) ; x_bar = proj_[l,u] zt ;
@@ -526,19 +502,12 @@ struct XPhaseOp : OpBase {
     }
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
-    // The five operands of a row's epilogue are requested before phase 1 (HPR_STAGE_OPERANDS): ncu put 16 % of the x-phase's
-    // stall samples on the instructions that wait for them after the row sums.
-    static constexpr int kStage = HPR_STAGE_OPERANDS ? 5 : 0;
-    __device__ __forceinline__ void stage(int j, double *s) const {
-        cp_async8(s, x + j); cp_async8(s + 32, c + j); cp_async8(s + 64, l + j); cp_async8(s + 96, u + j); cp_async8(s + 128, x0 + j);
-    }
-    __device__ __forceinline__ void row_staged(int j, const double (&acc)[1], const double *s) const { apply(j, acc[0], s[0], s[32], s[64], s[96], s[128]); }
-    __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const { apply(j, acc[0], x[j], c[j], l[j], u[j], x0[j]); }
-    __device__ __forceinline__ void apply(int j, double w, double xi, double cj, double lj, double uj, double x0j) const {
-        const double zt = fma(sigma, w - cj, xi);
-        const double xb = fmin(uj, fmax(lj, zt));
+    __device__ __forceinline__ void row(int j, const double (&acc)[1], long long, long long) const {
+        const double xi = x[j];
+        const double zt = fma(sigma, acc[0] - c[j], xi);
+        const double xb = fmin(u[j], fmax(l[j], zt));
         const double xh = 2.0 * xb - xi;
-        x[j] = fma(f2, xh, f1 * x0j);
+        x[j] = fma(f2, xh, f1 * x0[j]);
         x_hat[j] = xh;
         if (CHECK) {
             x_bar[j] = xb;
@@ -578,18 +547,13 @@ struct YPhaseOp : OpBase {
     }
     __device__ __forceinline__ void elem(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER == 1) ? g_tex(col) : g_lsu(col)); }
     __device__ __forceinline__ void elem_b(double v, int col, double (&o)[1]) const { o[0] = v * ((TEX && HPR_TEX_GATHER >= 1) ? g_tex(col) : g_lsu(col)); }
-    static constexpr int kStage = HPR_STAGE_OPERANDS ? 4 : 0;
-    __device__ __forceinline__ void stage(int i, double *s) const {
-        cp_async8(s, y + i); cp_async8(s + 32, AL + i); cp_async8(s + 64, AU + i); cp_async8(s + 96, y0 + i);
-    }
-    __device__ __forceinline__ void row_staged(int i, const double (&acc)[1], const double *s) const { apply(i, acc[0], s[0], s[32], s[64], s[96]); }
-    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const { apply(i, acc[0], y[i], AL[i], AU[i], y0[i]); }
-    __device__ __forceinline__ void apply(int i, double w, double yi, double ALi, double AUi, double y0i) const {
-        const double v = fma(-lamsig, yi, w);
-        const double d = fmax(ALi - v, fmin(AUi - v, 0.0));
+    __device__ __forceinline__ void row(int i, const double (&acc)[1], long long, long long) const {
+        const double yi = y[i];
+        const double v = fma(-lamsig, yi, acc[0]);
+        const double d = fmax(AL[i] - v, fmin(AU[i] - v, 0.0));
         const double yb = inv_lamsig * d;
         const double yh = 2.0 * yb - yi;
-        y[i] = fma(f2, yh, f1 * y0i);
+        y[i] = fma(f2, yh, f1 * y0[i]);
         if (CHECK) {
             y_bar[i] = yb;
             y_obj[i] = v + d;
