@@ -49,6 +49,9 @@ constexpr int kWarps = kThreads / 32;
 #ifndef HPR_MIN_BLOCKS
 #define HPR_MIN_BLOCKS 6
 #endif
+#ifndef HPR_META_LATE
+#define HPR_META_LATE 1   // row metadata requested behind the first round of the nonzero stream (0: in front of it)
+#endif
 #ifndef HPR_TEX_GATHER
 #define HPR_TEX_GATHER 1
 #endif
@@ -249,15 +252,21 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
     const long long s = (long long)item * kWarpChunk;
     const long long e = (s + kWarpChunk < M.nnz) ? s + kWarpChunk : (s < M.nnz ? M.nnz : s);
 
-    // row metadata of the first batch: requested before the nonzeros so its latency overlaps phase 1
-    const int rA = __ldg(M.item_row + item);
-    const int rB = __ldg(M.item_row + item + 1);
-    const int r_last = (rB < M.rows) ? rB : M.rows - 1;   // last row touched (rB included: it may start here)
+    // Row metadata of the first batch.  item_row -> rowPtr is a chain of two dependent loads: it is requested BEHIND the
+    // first round of the nonzero stream (HPR_META_LATE), so that the warp does not sit on item_row's round trip with
+    // nothing else in flight (ncu: 6 % of the x-phase's stall samples were on the address arithmetic that waits for it).
+    int rA = 0, rB = 0, r_last = -1;
     long long p0 = 0, p1 = 0;
-    if (rA + lane <= r_last) {
-        p0 = (long long)M.rowPtr[rA + lane];
-        p1 = (long long)M.rowPtr[rA + lane + 1];
-    }
+    auto load_row_meta = [&]() {
+        rA = __ldg(M.item_row + item);
+        rB = __ldg(M.item_row + item + 1);
+        r_last = (rB < M.rows) ? rB : M.rows - 1;   // last row touched (rB included: it may start here)
+        if (rA + lane <= r_last) {
+            p0 = (long long)M.rowPtr[rA + lane];
+            p1 = (long long)M.rowPtr[rA + lane + 1];
+        }
+    };
+    if (!HPR_META_LATE || HPR_BULK_STREAM) load_row_meta();
 
     // ---- phase 1: stream nonzeros, gather, multiply (kRoundNnz loads in flight per lane) -----------
 #if HPR_BULK_STREAM
@@ -300,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, HPR_MIN_BLOCKS) csr_stream_kernel(Cs
                 cc[u] = ld_stream(c2 + t);
                 vv[u] = ld_stream(v2 + t);
             }
+            if (HPR_META_LATE && !HPR_BULK_STREAM && rd == 0) load_row_meta();
 #pragma unroll
             for (int u = 0; u < kRoundNnz / 2; ++u) {
                 double o0[NV], o1[NV];
