@@ -18,7 +18,7 @@ r = eng.solve_partitioned_synth(a.m, a.n, a.k, p, n_gpus=a.gpus, want_solution=F
 wall = time.perf_counter() - t0
 i = r["info"]
 nnz = a.m * a.k
-print(json.dumps(dict(config="configs[4]: synthetic uniform LP, row-block partitioned with NCCL over NVLink", m=a.m, n=a.n, nnz=nnz, gpus=a.gpus,
+print(json.dumps(dict(config="configs[4]: synthetic uniform LP, row-block partitioned over NVLink (peer-memory exchange)", m=a.m, n=a.n, nnz=nnz, gpus=a.gpus,
                       status=r["status"], iters=r["iter"], primal_obj=r["primal_obj"], obj_star=r["obj_star"], residuals=r["residuals"],
                       wall_s=wall, generate_and_transpose_s=i["setup_seconds"], scaling_s=i["scaling_seconds"], power_s=i["power_seconds"],
                       power_iters=i["power_iters"], solver_time_s=r["time"], loop_ms=i["loop_device_ms"],
