@@ -37,6 +37,32 @@ def test_synthetic_lp_reaches_constructed_optimum(pkg, oracle, kind, m, n, nnz):
     assert abs(r["primal_obj"] - lp["obj_star"]) / (1 + abs(lp["obj_star"])) < 1e-5
 
 
+@pytest.mark.parametrize("kind", ["banded", "blocked"])
+def test_structured_twins_of_the_synthetic_lp(pkg, oracle, kind):
+    """The structured generators behind bench.py's c3band / c3block workloads: sorted distinct columns inside the window,
+    dense 8x8 blocks for 'blocked' (the 8 rows of a group share their columns, which come in aligned runs of 8), and an LP
+    the oracle solves to the constructed optimum like the uniform ones."""
+    m, n, per_row = 640, 6000, 24
+    lp = pkg.synth_lp(kind, m, n, m * per_row, with_solution=True)
+    rp, col = lp["rowPtr"], lp["colIndex"]
+    assert rp[-1] == m * per_row and col.min() >= 0 and col.max() < n
+    for i in range(m):
+        c = col[rp[i]:rp[i + 1]]
+        assert np.all(np.diff(c) > 0)
+        assert c[-1] - c[0] < 4096
+    if kind == "blocked":
+        for g in range(0, m, 8):
+            first = col[rp[g]:rp[g + 1]]
+            assert np.all(first % 8 == np.arange(per_row) % 8) and np.all(first[::8] % 8 == 0)   # aligned runs of 8
+            for i in range(g + 1, g + 8):
+                assert np.array_equal(col[rp[i]:rp[i + 1]], first)
+        lens = np.bincount(col, minlength=n)
+        assert np.all(lens % 8 == 0)            # column counts are multiples of 8: the uneven rows of the transpose
+    r = oracle.solve(lp, pkg.Parameters.default(stop_tol=1e-6))
+    assert r["status"] == "OPTIMAL"
+    assert abs(r["primal_obj"] - lp["obj_star"]) / (1 + abs(lp["obj_star"])) < 1e-5
+
+
 def test_iter_limit_and_stale_bar_quirk(pkg, oracle):
     lp = pkg.synth_lp("uniform", 120, 400, 120 * 10)
     r = oracle.solve(lp, pkg.Parameters.default(max_iter=40, stop_tol=1e-12))
