@@ -69,19 +69,40 @@ class NameMap {
     void assign(const Tok &k, int v) {   // insert or overwrite (a repeated ROWS name re-binds, as operator[] does)
         if (int *p = find(k)) { *p = v; return; }
         if ((count_ + 1) * 2 > slots_.size()) rehash(slots_.size() * 2);
-        place(k, v);
+        place(k, hash(k), v);
         ++count_;
     }
-
-  private:
-    struct Slot { const char *p = nullptr; int len = 0; int val = 0; };
+    // The same with the hash computed elsewhere (the COLUMNS sweep hashes the names in parallel) and the table sized up
+    // front, so that the one sequential pass over ~n column names neither rehashes nor waits on a cold slot.
     static size_t hash(const Tok &k) {
         uint64_t h = 1469598103934665603ull;
         for (int i = 0; i < k.len; ++i) { h ^= (unsigned char)k.p[i]; h *= 1099511628211ull; }
         return (size_t)(h ^ (h >> 29));
     }
-    void place(const Tok &k, int v) {
-        size_t i = hash(k) & mask_;
+    void reserve(size_t names) {
+        size_t cap = slots_.size();
+        while ((count_ + names + 1) * 2 > cap) cap *= 2;
+        if (cap != slots_.size()) rehash(cap);
+    }
+    void prefetch(size_t h) const { __builtin_prefetch(&slots_[h & mask_]); }
+    int *find(const Tok &k, size_t h) {
+        size_t i = h & mask_;
+        while (slots_[i].p) {
+            if (slots_[i].len == k.len && std::memcmp(slots_[i].p, k.p, k.len) == 0) return &slots_[i].val;
+            i = (i + 1) & mask_;
+        }
+        return nullptr;
+    }
+    void insert_new(const Tok &k, size_t h, int v) {   // k is known to be absent
+        if ((count_ + 1) * 2 > slots_.size()) rehash(slots_.size() * 2);
+        place(k, h, v);
+        ++count_;
+    }
+
+  private:
+    struct Slot { const char *p = nullptr; int len = 0; int val = 0; };
+    void place(const Tok &k, size_t h, int v) {
+        size_t i = h & mask_;
         while (slots_[i].p) i = (i + 1) & mask_;
         slots_[i].p = k.p; slots_[i].len = k.len; slots_[i].val = v;
     }
@@ -91,13 +112,18 @@ class NameMap {
         slots_.assign(cap, Slot());
         mask_ = cap - 1;
         for (const Slot &s : old)
-            if (s.p) place(Tok{s.p, s.len}, s.val);
+            if (s.p) place(Tok{s.p, s.len}, hash(Tok{s.p, s.len}), s.val);
     }
     std::vector<Slot> slots_;
     size_t mask_ = 0, count_ = 0;
 };
 
-struct Coo { int row, col; double val; };
+struct Coo {
+    int row, col;
+    double val;
+    Coo() {}   // deliberately uninitialised: vectors of entries are resized and then filled by several threads (first touch in parallel)
+    Coo(int r, int c, double v) : row(r), col(c), val(v) {}
+};
 
 struct MpsData {
     NameMap row_index;                                 // 0 objective, -1 rim objective, k+1 constraint k
@@ -196,6 +222,7 @@ struct ColEvent {
     int lineno;        // line number inside the block (1-based), made global by the caller
     int nf;            // SHORT: number of fields
     int col;           // RUN: column index (sequential pass)
+    size_t hash;       // RUN: NameMap::hash(name), computed in the parallel sweep
 };
 struct ColChunk {
     const char *b, *e;
@@ -241,13 +268,13 @@ void parse_columns_block(MpsData &d, const char *b, const char *e, int lineno_ba
                 if (nf > 0) {
                     if (nf >= 3 && f[1].is("'MARKER'")) {
                         ColEvent ev{f[2].is("'INTORG'") ? ColEvent::INTORG : (f[2].is("'INTEND'") ? ColEvent::INTEND : ColEvent::BAD_MARKER),
-                                    f[2], p, ln, nf, -1};
+                                    f[2], p, ln, nf, -1, 0};
                         c.events.push_back(ev);
                     } else if (nf < 3) {
-                        c.events.push_back(ColEvent{ColEvent::SHORT, Tok(), p, ln, nf, -1});
+                        c.events.push_back(ColEvent{ColEvent::SHORT, Tok(), p, ln, nf, -1, 0});
                     } else if (!have_cur || !cur.same(f[0])) {
                         cur = f[0]; have_cur = true;
-                        c.events.push_back(ColEvent{ColEvent::RUN, f[0], p, ln, nf, -1});
+                        c.events.push_back(ColEvent{ColEvent::RUN, f[0], p, ln, nf, -1, NameMap::hash(f[0])});
                     }
                 }
             }
@@ -261,8 +288,19 @@ void parse_columns_block(MpsData &d, const char *b, const char *e, int lineno_ba
     const double NaN = std::nan("");
     std::vector<int> base(T + 1, 0);
     for (int t = 0; t < T; ++t) base[t + 1] = base[t] + ch[t].lines;
+    {   // at most one new column per event: size the table and the column arrays once
+        size_t nev = 0;
+        for (int t = 0; t < T; ++t) nev += ch[t].events.size();
+        d.col_index.reserve(nev);
+        d.c.reserve(d.c.size() + nev); d.lvar.reserve(d.lvar.size() + nev); d.uvar.reserve(d.uvar.size() + nev);
+        d.marked.reserve(d.marked.size() + nev);
+    }
+    constexpr size_t kAhead = 16;   // slots of the events this far ahead are prefetched (the table is tens of MB)
     for (int t = 0; t < T; ++t) {
-        for (ColEvent &ev : ch[t].events) {
+        std::vector<ColEvent> &evs = ch[t].events;
+        for (size_t i = 0; i < evs.size(); ++i) {
+            if (i + kAhead < evs.size() && evs[i + kAhead].kind == ColEvent::RUN) d.col_index.prefetch(evs[i + kAhead].hash);
+            ColEvent &ev = evs[i];
             const int lineno = lineno_base + base[t] + ev.lineno;
             switch (ev.kind) {
                 case ColEvent::INTORG: *integer_section = true; break;
@@ -270,10 +308,10 @@ void parse_columns_block(MpsData &d, const char *b, const char *e, int lineno_ba
                 case ColEvent::BAD_MARKER: std::cerr << "Error: Ignoring marker " << ev.name.str() << " at line " << lineno << "\n"; break;
                 case ColEvent::SHORT: std::cerr << "Error: Line " << lineno << " contains only " << ev.nf << " fields\n"; break;
                 case ColEvent::RUN: {
-                    if (int *it = d.col_index.find(ev.name)) ev.col = *it;
+                    if (int *it = d.col_index.find(ev.name, ev.hash)) ev.col = *it;
                     else {
                         ev.col = (int)d.c.size();
-                        d.col_index.assign(ev.name, ev.col);
+                        d.col_index.insert_new(ev.name, ev.hash, ev.col);
                         d.c.push_back(0.0); d.lvar.push_back(NaN); d.uvar.push_back(NaN);
                         d.marked.push_back(*integer_section ? 1 : 0);
                     }
@@ -324,11 +362,13 @@ void parse_columns_block(MpsData &d, const char *b, const char *e, int lineno_ba
         }
     }
     const double tt3 = wall();
-    size_t total = d.entries.size();
-    for (int t = 0; t < T; ++t) total += ch[t].entries.size();
-    d.entries.reserve(total);
+    std::vector<size_t> off(T + 1, d.entries.size());
+    for (int t = 0; t < T; ++t) off[t + 1] = off[t] + ch[t].entries.size();
+    d.entries.resize(off[T]);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t)
+        if (!ch[t].entries.empty()) std::memcpy(static_cast<void *>(d.entries.data() + off[t]), ch[t].entries.data(), sizeof(Coo) * ch[t].entries.size());
     for (int t = 0; t < T; ++t) {
-        d.entries.insert(d.entries.end(), ch[t].entries.begin(), ch[t].entries.end());
         for (const auto &o : ch[t].obj) d.c[o.first] = o.second;
         for (const auto &u : ch[t].unknown_rows)
             std::cerr << "Error: Unknown row " << u.second << " at line " << (lineno_base + base[t] + u.first) << "\n";
@@ -584,11 +624,17 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp) {
     if (g_timing) std::fprintf(stderr, "[hprlp timing] sorted at %.3f s (%zu duplicate cards)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), n_dup);
     std::vector<int> cols; std::vector<double> vals;
     std::vector<int> rowptr((size_t)m + 1, 0);
+    int *direct_cols = nullptr;      // no duplicate cards: the model's arrays are filled straight from the sorted list by all
+    double *direct_vals = nullptr;   // threads (no intermediate vectors, no single-threaded 12 B/nnz copy)
     if (n_dup == 0) {
         // no duplicate (row, col) card: the sorted list IS the CSR matrix
-        cols.resize(ne); vals.resize(ne);
+        if (m > 0 && n > 0 && ne > 0) {
+            direct_cols = static_cast<int *>(std::malloc(sizeof(int) * ne));
+            direct_vals = static_cast<double *>(std::malloc(sizeof(double) * ne));
+            if (!direct_cols || !direct_vals) { std::free(direct_cols); std::free(direct_vals); throw std::bad_alloc(); }
 #pragma omp parallel for schedule(static)
-        for (long long k = 0; k < (long long)ne; ++k) { cols[k] = sorted[k].col; vals[k] = sorted[k].val; }
+            for (long long k = 0; k < (long long)ne; ++k) { direct_cols[k] = sorted[k].col; direct_vals[k] = sorted[k].val; }
+        }
         for (int i = 0; i <= m; ++i) rowptr[i] = (int)start[i];
     } else {
         cols.reserve(ne); vals.reserve(ne);
@@ -610,7 +656,7 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp) {
         }
         while (row < m) { row++; rowptr[row] = (int)vals.size(); }
     }
-    const int nnz = (int)vals.size();
+    const int nnz = direct_cols ? (int)ne : (int)vals.size();
     if (m <= 0 || n <= 0 || nnz <= 0) {
         std::cerr << "Error: Invalid dimensions in build_model_from_arrays: m=" << m << ", n=" << n << ", nnz=" << nnz << std::endl;
         return false;
@@ -620,11 +666,16 @@ bool build_model_from_mps(const char *path, LP_info_cpu *lp) {
     lp->A = static_cast<sparseMatrix *>(std::malloc(sizeof(sparseMatrix)));
     lp->A->row = m; lp->A->col = n; lp->A->numElements = nnz;
     lp->A->rowPtr = static_cast<int *>(std::malloc(sizeof(int) * ((size_t)m + 1)));
-    lp->A->colIndex = static_cast<int *>(std::malloc(sizeof(int) * (size_t)nnz));
-    lp->A->value = static_cast<double *>(std::malloc(sizeof(double) * (size_t)nnz));
     std::memcpy(lp->A->rowPtr, rowptr.data(), sizeof(int) * ((size_t)m + 1));
-    std::memcpy(lp->A->colIndex, cols.data(), sizeof(int) * (size_t)nnz);
-    std::memcpy(lp->A->value, vals.data(), sizeof(double) * (size_t)nnz);
+    if (direct_cols) {
+        lp->A->colIndex = direct_cols;
+        lp->A->value = direct_vals;
+    } else {
+        lp->A->colIndex = static_cast<int *>(std::malloc(sizeof(int) * (size_t)nnz));
+        lp->A->value = static_cast<double *>(std::malloc(sizeof(double) * (size_t)nnz));
+        std::memcpy(lp->A->colIndex, cols.data(), sizeof(int) * (size_t)nnz);
+        std::memcpy(lp->A->value, vals.data(), sizeof(double) * (size_t)nnz);
+    }
     auto dup = [](const std::vector<double> &v) {
         double *q = static_cast<double *>(std::malloc(sizeof(double) * std::max<size_t>(v.size(), 1)));
         std::memcpy(q, v.data(), sizeof(double) * v.size());
